@@ -1,0 +1,116 @@
+// context.h — the per-GPU context behind the C ABI (include/zkb.h): stream, scratch, cached
+// NTT tables and MSM work buffers.  Internal to libzkb.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkb.h"
+#include "host_ff.hpp"
+#include "msm.h"
+#include "ntt.h"
+
+namespace zkb {
+
+// grow-only device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct NttDomain {          // everything that depends on (log_n, direction)
+  uint32_t log_n = 0;
+  std::vector<uint32_t> ks; // pass widths
+  DevBuf tw_lo, tw_hi, tw_hi_ninv;
+  uint32_t lo_bits = 0;
+  std::vector<DevBuf> full; // optional full tables, one per column pass (last one folds 1/n? no: pass 0)
+  bool full_ready = false;
+};
+
+struct CosetTables {        // per log_n
+  DevBuf fwd;               // g^i
+  DevBuf inv;               // g^{-i} / n
+  DevBuf inv_z;             // g^{-i} / (n * (g^n - 1))     (Groth16 H pass)
+  DevBuf ninv;              // constant 1/n (single-pass inverse)
+};
+
+struct MsmScratch {
+  DevBuf keys_in, vals_in, keys_out, vals_out, sort_temp, m_valid, buckets, part1_keys,
+      part1_pts, part2_keys, part2_pts, group_sums, window_sums, result_xyzz, result_affine;
+};
+
+}  // namespace zkb
+
+struct zkb_bases {
+  int device = 0;
+  int is_g2 = 0;
+  uint64_t n = 0;
+  void* d_pts = nullptr;    // affine Montgomery, 64 / 128 B per point
+};
+
+struct zkb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;
+  int64_t msm_window = 0;
+  int64_t ntt_full_twiddles = 0;
+
+  zkb::DevBuf stage_fwd, stage_inv;        // 255-entry stage twiddle tables
+  std::map<uint64_t, zkb::NttDomain*> domains;   // key = log_n * 2 + inverse
+  std::map<uint32_t, zkb::CosetTables*> cosets;
+  zkb::DevBuf ntt_tmp;                     // ping-pong buffer of the multi-pass NTT
+  zkb::DevBuf io_a, io_b, io_c;            // staging for the host-buffer entry points
+  zkb::MsmScratch msm;
+};
+
+namespace zkb {
+
+// RAII guard implementing the "one call at a time per ctx" rule
+struct BusyGuard {
+  zkb_ctx* c;
+  bool ok;
+  explicit BusyGuard(zkb_ctx* ctx) : c(ctx), ok(!ctx->busy.test_and_set()) {}
+  ~BusyGuard() { if (ok) c->busy.clear(); }
+};
+
+int set_error(zkb_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(zkb_ctx* ctx, cudaError_t e, const char* what);
+
+#define ZKB_CUDA(ctx, expr)                                                   \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return ::zkb::cuda_fail((ctx), _e, #expr);         \
+  } while (0)
+
+// internal device-level entry points (used by the C ABI wrappers and by the Groth16 pipeline)
+int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
+            const void* pre_scale, const void* post_scale, int fold_ninv, int mont_in,
+            int mont_out);
+int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out);
+int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
+             void* d_out_affine);
+int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g2, void* d_out);
+
+void host_fr_root(uint32_t log_n, int inverse, uint32_t out_mont[8]);
+
+}  // namespace zkb

@@ -1,0 +1,439 @@
+// ff.cuh — BN254 Fq / Fr Montgomery arithmetic on 8x32-bit limbs for sm_100a.
+//
+// Replaces (there is no reference code for it — SURVEY.md §8(a) row a13): the field layer of
+// the external prover eigen-zeth reaches through GenFinalProofRequest
+// (reference proto/prover/v1/prover.proto:130-148).
+//
+// Representation: little-endian limbs, Montgomery form (x*2^256 mod p), *lazily reduced*:
+// every value that crosses a function boundary is in [0, 2p).  Because p < 2^254, 4p < 2^256,
+// so a+b never carries out of 256 bits and the Montgomery product of two values < 2p is again
+// < 2p without a final subtraction:  (ab + mp)/2^256 < 4p^2/2^256 + p < 2p.
+//
+// The multiplier is a two-lane CIOS: partial products a_j*b_i with j even are 64-bit aligned on
+// even limb positions, those with j odd on odd positions, so every `mad.lo.cc/madc.hi.cc` pair
+// is one IMAD.WIDE.U32 with carry-in/out and each lane is a single uninterrupted carry chain.
+// After the reduction step the low limb of the even lane is zero; dividing by 2^32 swaps the
+// roles of the two lanes.  Every carry chain lives inside ONE asm statement, so the compiler
+// can never schedule anything between a carry producer and its consumer.
+#pragma once
+#include <cstdint>
+
+namespace zkb {
+
+struct FqParams {
+  static constexpr uint32_t M0 = 0xe4866389u;  // -q^{-1} mod 2^32
+  __host__ __device__ static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t mod2(int i) {
+    constexpr uint32_t m[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u,
+                               0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t one(int i) {  // 2^256 mod q
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t r2(int i) {  // 2^512 mod q
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+};
+
+struct FrParams {
+  static constexpr uint32_t M0 = 0xefffffffu;  // -r^{-1} mod 2^32
+  __host__ __device__ static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t mod2(int i) {
+    constexpr uint32_t m[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u,
+                               0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t one(int i) {  // 2^256 mod r
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  __host__ __device__ static constexpr uint32_t r2(int i) {  // 2^512 mod r
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+};
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------- carry-chain building blocks
+// lane[0..7] = {a0,a1,a2,a3} (x) b   as four disjoint 64-bit products (no carries needed)
+__device__ __forceinline__ void lane_mul(uint32_t (&l)[8], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b) {
+  asm("mul.lo.u32 %0, %8, %12;\n\t"
+      "mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12;\n\t"
+      "mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12;\n\t"
+      "mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12;\n\t"
+      "mul.hi.u32 %7, %11, %12;"
+      : "=&r"(l[0]), "=&r"(l[1]), "=&r"(l[2]), "=&r"(l[3]), "=&r"(l[4]), "=&r"(l[5]), "=&r"(l[6]),
+        "=&r"(l[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// lane += {a0..a3} (x) b as one carry chain; the carry out of lane[7] is added to `spill`
+// (spill is the top limb of the other lane, which sits one limb position higher).
+__device__ __forceinline__ void lane_mad_spill(uint32_t (&l)[8], uint32_t& spill, uint32_t a0,
+                                               uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(l[0]), "+r"(l[1]), "+r"(l[2]), "+r"(l[3]), "+r"(l[4]), "+r"(l[5]), "+r"(l[6]),
+        "+r"(l[7]), "+r"(spill)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// lane += {a0..a3} (x) b; the caller guarantees the sum fits (no carry out of lane[7]).
+__device__ __forceinline__ void lane_mad(uint32_t (&l)[8], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(l[0]), "+r"(l[1]), "+r"(l[2]), "+r"(l[3]), "+r"(l[4]), "+r"(l[5]), "+r"(l[6]),
+        "+r"(l[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// The lane `y` has just been the even lane of a reduction step: y[0]==0 and, after the division
+// by 2^32, y[1] sits at position 0 (it belongs to the new even lane `x`), y[2..7] at positions
+// 1..6.  This fuses  x[0] += y[1]  (carry into position 1) with
+//   y_new[0..7] = (y[2..7],0,0) + {a0..a3} (x) b      (positions 1..8, cannot overflow).
+__device__ __forceinline__ void lane_shift_mad(uint32_t& x0, uint32_t (&y)[8], uint32_t a0,
+                                               uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm("add.cc.u32 %0, %0, %2;\n\t"
+      "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+      "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+      "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+      "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+      "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+      "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+      "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+      "madc.hi.u32 %8, %12, %13, 0;"
+      : "+r"(x0), "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]),
+        "+r"(y[6]), "+r"(y[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// One Montgomery reduction step on (even lane e @ positions 0..7, odd lane o @ positions 1..8):
+// adds m*p with m = e[0]*M0 so that e[0] becomes 0.
+template <class P>
+__device__ __forceinline__ void redc_step(uint32_t (&e)[8], uint32_t (&o)[8]) {
+  uint32_t m = e[0] * P::M0;
+  lane_mad(o, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+  lane_mad_spill(e, o[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+}
+
+template <class P>
+__device__ __forceinline__ void mont_mul(uint32_t (&r)[8], const uint32_t (&a)[8],
+                                         const uint32_t (&b)[8]) {
+  uint32_t e[8], o[8];
+  lane_mul(e, a[0], a[2], a[4], a[6], b[0]);
+  lane_mul(o, a[1], a[3], a[5], a[7], b[0]);
+  redc_step<P>(e, o);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    // odd i: o is the even-aligned lane, e the one being shifted
+    lane_shift_mad(o[0], e, a[1], a[3], a[5], a[7], b[i]);
+    lane_mad_spill(o, e[7], a[0], a[2], a[4], a[6], b[i]);
+    redc_step<P>(o, e);
+    if (i + 1 < 8) {
+      lane_shift_mad(e[0], o, a[1], a[3], a[5], a[7], b[i + 1]);
+      lane_mad_spill(e, o[7], a[0], a[2], a[4], a[6], b[i + 1]);
+      redc_step<P>(e, o);
+    }
+  }
+  // after i = 7 the lane with a zero low limb is o: result = e + (o >> 32)
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]),
+        "=&r"(r[7])
+      : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+        "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+}
+
+// r = a + b (256-bit, no carry out by the 4p < 2^256 invariant)
+__device__ __forceinline__ void add256(uint32_t (&r)[8], const uint32_t (&a)[8],
+                                       const uint32_t (&b)[8]) {
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]),
+        "=&r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+
+// r = a - b (256-bit), returns the borrow as 0 / 0xffffffff
+__device__ __forceinline__ uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)[8],
+                                           const uint32_t (&b)[8]) {
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]),
+        "=&r"(r[7]), "=&r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return borrow;
+}
+
+// ---------------------------------------------------------------- the field type
+template <class P>
+struct Fp {
+  uint32_t v[8];
+  using Params = P;
+
+  __device__ __forceinline__ static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  __device__ __forceinline__ static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  __device__ __forceinline__ static Fp modulus() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::mod(i);
+    return r;
+  }
+  __device__ __forceinline__ static Fp modulus2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::mod2(i);
+    return r;
+  }
+  __device__ __forceinline__ static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+
+  // 128-bit vectorised global/shared access (pointer must be 16-byte aligned)
+  __device__ __forceinline__ static Fp load(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = q[0], hi = q[1];
+    Fp r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+  }
+  __device__ __forceinline__ static Fp load_nc(const void* p) {  // read-only path
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fp r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(void* p) const {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    q[1] = make_uint4(v[4], v[5], v[6], v[7]);
+  }
+
+  // [0,4p) -> [0,2p)
+  __device__ __forceinline__ void fold2p() {
+    uint32_t t[8];
+    uint32_t m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m2[i] = P::mod2(i);
+    uint32_t borrow = sub256(t, v, m2);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = borrow ? v[i] : t[i];
+  }
+  // [0,2p) -> [0,p)   (canonical residue)
+  __device__ __forceinline__ Fp reduced() const {
+    uint32_t t[8];
+    uint32_t m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+    uint32_t borrow = sub256(t, v, m);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? v[i] : t[i];
+    return r;
+  }
+
+  __device__ __forceinline__ friend Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    add256(r.v, a.v, b.v);
+    r.fold2p();
+    return r;
+  }
+  __device__ __forceinline__ friend Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    uint32_t borrow = sub256(r.v, a.v, b.v);
+    uint32_t m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m2[i] = P::mod2(i) & borrow;
+    uint32_t t[8];
+    add256(t, r.v, m2);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    return r;
+  }
+  __device__ __forceinline__ friend Fp operator*(const Fp& a, const Fp& b) {
+    Fp r;
+    mont_mul<P>(r.v, a.v, b.v);
+    return r;
+  }
+  __device__ __forceinline__ Fp sqr() const { return (*this) * (*this); }
+  __device__ __forceinline__ Fp dbl() const { return (*this) + (*this); }
+  __device__ __forceinline__ Fp neg() const { return zero() - (*this); }
+
+  // value == 0 mod p for a lazily reduced value: the only representatives are 0 and p
+  __device__ __forceinline__ bool is_zero() const {
+    uint32_t o = 0, x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o |= v[i];
+      x |= v[i] ^ P::mod(i);
+    }
+    return o == 0 || x == 0;
+  }
+  __device__ __forceinline__ bool raw_is_zero() const {  // all limbs zero (encoding tests)
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  __device__ __forceinline__ friend bool operator==(const Fp& a, const Fp& b) {
+    return (a - b).is_zero();
+  }
+
+  // canonical integer <-> Montgomery
+  __device__ __forceinline__ Fp to_mont() const { return (*this) * r2(); }
+  __device__ __forceinline__ Fp from_mont() const {
+    Fp o = zero();
+    o.v[0] = 1;
+    return ((*this) * o).reduced();
+  }
+
+  // a^e for a 256-bit little-endian exponent (not constant time; used for inversion only)
+  __device__ Fp pow(const uint32_t (&e)[8]) const {
+    Fp r = one();
+    for (int i = 255; i >= 0; i--) {
+      r = r.sqr();
+      if ((e[i >> 5] >> (i & 31)) & 1) r = r * (*this);
+    }
+    return r;
+  }
+  // Fermat inversion; 0 -> 0
+  __device__ Fp inverse() const {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2;  // both moduli have low limb >= 2
+    return pow(e);
+  }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+// ---------------------------------------------------------------- Fq2 = Fq[u]/(u^2+1)
+struct Fq2 {
+  Fq c0, c1;
+  __device__ __forceinline__ static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+  __device__ __forceinline__ static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+  __device__ __forceinline__ static Fq2 load(const void* p) {
+    const char* c = reinterpret_cast<const char*>(p);
+    return {Fq::load(c), Fq::load(c + 32)};
+  }
+  __device__ __forceinline__ static Fq2 load_nc(const void* p) {
+    const char* c = reinterpret_cast<const char*>(p);
+    return {Fq::load_nc(c), Fq::load_nc(c + 32)};
+  }
+  __device__ __forceinline__ void store(void* p) const {
+    char* c = reinterpret_cast<char*>(p);
+    c0.store(c);
+    c1.store(c + 32);
+  }
+  __device__ __forceinline__ friend Fq2 operator+(const Fq2& a, const Fq2& b) {
+    return {a.c0 + b.c0, a.c1 + b.c1};
+  }
+  __device__ __forceinline__ friend Fq2 operator-(const Fq2& a, const Fq2& b) {
+    return {a.c0 - b.c0, a.c1 - b.c1};
+  }
+  // Karatsuba: 3 Fq multiplications
+  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) {
+    Fq t0 = a.c0 * b.c0;
+    Fq t1 = a.c1 * b.c1;
+    Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+    return {t0 - t1, t2 - t0 - t1};
+  }
+  // (a0+a1)(a0-a1), 2 a0 a1 : 2 Fq multiplications
+  __device__ __forceinline__ Fq2 sqr() const {
+    Fq t = c0 * c1;
+    return {(c0 + c1) * (c0 - c1), t.dbl()};
+  }
+  __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+  __device__ __forceinline__ Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+  __device__ __forceinline__ bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  __device__ __forceinline__ bool raw_is_zero() const {
+    return c0.raw_is_zero() && c1.raw_is_zero();
+  }
+  __device__ __forceinline__ friend bool operator==(const Fq2& a, const Fq2& b) {
+    return (a - b).is_zero();
+  }
+  __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
+  __device__ __forceinline__ Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
+  __device__ __forceinline__ Fq2 reduced() const { return {c0.reduced(), c1.reduced()}; }
+  __device__ Fq2 inverse() const {
+    Fq d = (c0.sqr() + c1.sqr()).inverse();
+    return {c0 * d, (c1 * d).neg()};
+  }
+};
+
+#endif  // __CUDACC__
+}  // namespace zkb

@@ -1,0 +1,54 @@
+// msm.h — plan / scratch descriptors shared by msm.cu and the context.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace zkb {
+
+struct MsmPlan {
+  int c;                    // window width (signed digits in [-2^{c-1}, 2^{c-1}])
+  uint32_t nwin;            // ceil(255 / c)
+  uint32_t half;            // buckets per window = 2^{c-1}
+  uint64_t n_buckets;       // nwin * half (also the sentinel key of zero digits)
+  uint64_t m;               // n * nwin (key, value) pairs
+  int key_bits;             // radix-sort key width
+  uint32_t l1_threads;      // chunks of the level-1 walk
+  uint32_t l2_len;          // chunk length of the level-2 walk
+  uint32_t l2_threads;
+  uint32_t gsize;           // buckets per reduce group
+  uint32_t groups_per_win;
+  uint32_t n_groups;
+  size_t point_bytes;       // sizeof(XYZZ)
+  size_t sort_temp_bytes;
+};
+
+struct MsmBuffers {
+  uint32_t *keys_in, *vals_in, *keys_out, *vals_out;  // m entries each
+  void* sort_temp;
+  uint64_t* m_valid;
+  void* buckets;            // n_buckets XYZZ
+  uint32_t* part1_keys;     // 2 * l1_threads
+  void* part1_pts;
+  uint32_t* part2_keys;     // 2 * l2_threads
+  void* part2_pts;
+  void* group_sums;         // n_groups XYZZ
+  void* window_sums;        // nwin XYZZ
+  void* result_xyzz;        // 1 XYZZ (Montgomery)
+  void* result_affine;      // 1 affine, canonical little-endian
+};
+
+MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count);
+void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                         cudaStream_t s);
+void msm_run_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                const void* d_bases, cudaStream_t s);
+void msm_run_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                const void* d_bases, cudaStream_t s);
+void msm_bases_to_mont_g1(void* d_pts, uint64_t n, cudaStream_t s);
+void msm_bases_to_mont_g2(void* d_pts, uint64_t n, cudaStream_t s);
+void msm_sum_affine_g1(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s);
+void msm_sum_affine_g2(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s);
+
+}  // namespace zkb

@@ -1,0 +1,108 @@
+// msm_common.cu — the curve-independent front half of the MSM pipeline: signed-digit extraction,
+// the (key, value) radix sort and the launch plan.  See msm_impl.cuh for the pipeline overview.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "msm.h"
+
+namespace zkb {
+
+// ---------------------------------------------------------------- 1. digits
+__global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t c,
+                                  uint32_t nwin, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals, uint32_t idx_base) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (1u << c) - 1;
+  const uint32_t sentinel = nwin * half;
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < nwin; w++) {
+    uint32_t bit = w * c;
+    uint32_t word = bit >> 5, sh = bit & 31;
+    uint32_t d = 0;
+    if (word < 8) {
+      uint64_t two = (uint64_t(s[word + 1]) << 32) | s[word];
+      d = uint32_t(two >> sh) & mask;
+    }
+    d += carry;
+    uint32_t neg = d > half;
+    uint32_t mag = neg ? (1u << c) - d : d;
+    carry = neg;
+    uint32_t key = mag ? w * half + (mag - 1) : sentinel;
+    keys[uint64_t(w) * n + i] = key;
+    vals[uint64_t(w) * n + i] = (idx_base + uint32_t(i)) | (neg << 31);
+  }
+}
+
+// first index whose key is >= limit in a sorted array (single thread, binary search)
+__global__ void msm_count_valid_kernel(const uint32_t* keys, uint64_t m, uint32_t limit,
+                                       uint64_t* out) {
+  uint64_t lo = 0, hi = m;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < limit) lo = mid + 1; else hi = mid;
+  }
+  *out = lo;
+}
+
+size_t msm_sort_temp_bytes(uint64_t m, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)m, 0,
+                                  end_bit);
+  return bytes;
+}
+
+MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count) {
+  MsmPlan p{};
+  int log_n = 0;
+  while ((1ull << log_n) < n) log_n++;
+  int c = c_override > 0 ? c_override : log_n - 6;
+  if (c_override <= 0) {
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+  }
+  p.c = c;
+  p.nwin = (255 + c - 1) / c;
+  p.half = 1u << (c - 1);
+  p.n_buckets = uint64_t(p.nwin) * p.half;
+  p.m = n * p.nwin;
+  p.key_bits = 1;
+  while ((1ull << p.key_bits) <= p.n_buckets) p.key_bits++;   // sentinel == n_buckets must fit
+  // level-1 threads: one resident wave, never less than 8 entries per thread
+  uint32_t per_sm = is_g2 ? 256 : 384;
+  uint64_t t1 = uint64_t(sm_count) * per_sm;
+  uint64_t cap = (p.m + 7) / 8;
+  if (cap < 1) cap = 1;
+  if (t1 > cap) t1 = cap;
+  p.l1_threads = uint32_t(t1);
+  p.l2_len = 32;
+  p.l2_threads = (2 * p.l1_threads + p.l2_len - 1) / p.l2_len;
+  p.gsize = p.half < 32 ? p.half : 32;
+  p.groups_per_win = p.half / p.gsize;
+  p.n_groups = p.groups_per_win * p.nwin;
+  p.point_bytes = is_g2 ? 256 : 128;
+  p.sort_temp_bytes = msm_sort_temp_bytes(p.m, p.key_bits);
+  return p;
+}
+
+
+void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                         cudaStream_t s) {
+  uint32_t blocks = uint32_t((n + 255) / 256);
+  if (blocks)
+    msm_digits_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, p.c,
+                                             p.nwin, b.keys_in, b.vals_in, 0);
+  size_t temp = p.sort_temp_bytes;
+  cub::DeviceRadixSort::SortPairs(b.sort_temp, temp, (const uint32_t*)b.keys_in, b.keys_out,
+                                  (const uint32_t*)b.vals_in, b.vals_out, (int64_t)p.m, 0,
+                                  p.key_bits, s);
+  msm_count_valid_kernel<<<1, 1, 0, s>>>(b.keys_out, p.m, uint32_t(p.n_buckets), b.m_valid);
+}
+
+}  // namespace zkb

@@ -1,0 +1,288 @@
+// msm_impl.cuh — signed-window Pippenger multi-scalar multiplication for BN254 G1 and G2 on sm_100a.
+//
+// No reference counterpart exists: these are the A/B1/L/H G1 MSMs
+// and the B2 G2 MSM of the Groth16 step behind reference proto/prover/v1/prover.proto:130-148.
+//
+// Pipeline (all on device, one stream):
+//   1. msm_digits        scalars -> signed radix-2^c digits; key = window*2^{c-1} + |d|-1,
+//                        value = point index | sign<<31; zero digits get the sentinel key.
+//   2. radix sort        (key,value) pairs by key (cub::DeviceRadixSort, key bits only).
+//   3. accumulate L1     the sorted stream is cut into equal chunks, one per thread; a thread
+//                        walks its chunk adding gathered affine points into an XYZZ accumulator.
+//                        Runs that lie strictly inside a chunk are whole buckets and are written
+//                        straight to the bucket array; the first and last run of a chunk are
+//                        emitted as (key, partial sum) pairs.  Work per thread is identical
+//                        whatever the bucket-size distribution is.
+//   4. accumulate L2     the same chunked walk over the partial list (XYZZ + XYZZ).
+//   5. finish            one thread per remaining run.
+//   6. bucket reduce     per group of 32 buckets: running sums, then weight by the group base.
+//   7. window sum        tree reduction of the group sums of each window.
+//   8. Horner            sum_w 2^{cw} S_w, conversion to affine, out of Montgomery form.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ec.cuh"
+#include "msm.h"
+
+namespace zkb {
+
+constexpr uint32_t kInvalidKey = 0xffffffffu;
+
+// ---------------------------------------------------------------- 3. accumulate, level 1
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate_l1_kernel(
+    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+    const uint64_t* __restrict__ m_valid_ptr, const Affine<F>* __restrict__ bases,
+    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
+    XYZZ<F>* __restrict__ part_pts, uint32_t n_threads) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const uint64_t m_valid = *m_valid_ptr;
+  const uint64_t len = (m_valid + n_threads - 1) / n_threads;
+  uint64_t start = uint64_t(tid) * len;
+  uint64_t end = start + len < m_valid ? start + len : m_valid;
+  if (start >= end) {
+    part_keys[2 * tid] = kInvalidKey;
+    part_keys[2 * tid + 1] = kInvalidKey;
+    return;
+  }
+  uint32_t key_n = keys[start], val_n = vals[start];
+  Affine<F> pt_n = Affine<F>::load_nc(bases + (val_n & 0x7fffffffu));
+  uint32_t cur = key_n;
+  bool first_run = true;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  for (uint64_t i = start; i < end; i++) {
+    uint32_t key = key_n, val = val_n;
+    Affine<F> pt = pt_n;
+    if (i + 1 < end) {
+      key_n = keys[i + 1];
+      val_n = vals[i + 1];
+      pt_n = Affine<F>::load_nc(bases + (val_n & 0x7fffffffu));
+    }
+    if (key != cur) {
+      if (first_run) {
+        part_keys[2 * tid] = cur;
+        acc.store(part_pts + 2 * tid);
+        first_run = false;
+      } else {
+        acc.store(buckets + cur);
+      }
+      acc = XYZZ<F>::infinity();
+      cur = key;
+    }
+    if (val >> 31) pt.y = pt.y.neg();
+    acc.madd(pt);
+  }
+  if (first_run) {
+    part_keys[2 * tid] = cur;
+    acc.store(part_pts + 2 * tid);
+    part_keys[2 * tid + 1] = kInvalidKey;
+  } else {
+    part_keys[2 * tid + 1] = cur;
+    acc.store(part_pts + 2 * tid + 1);
+  }
+}
+
+// ---------------------------------------------------------------- 4. accumulate, level 2
+// Same walk over a (key, XYZZ) list that may contain kInvalidKey holes.
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate_l2_kernel(
+    const uint32_t* __restrict__ keys, const XYZZ<F>* __restrict__ pts, uint32_t m, uint32_t len,
+    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
+    XYZZ<F>* __restrict__ part_pts, uint32_t n_threads) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  uint32_t start = tid * len;
+  uint32_t end = start + len < m ? start + len : m;
+  uint32_t cur = kInvalidKey;
+  bool first_run = true;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  part_keys[2 * tid] = kInvalidKey;
+  part_keys[2 * tid + 1] = kInvalidKey;
+  for (uint32_t i = start; i < end; i++) {
+    uint32_t key = keys[i];
+    if (key == kInvalidKey) continue;
+    if (cur == kInvalidKey) cur = key;
+    if (key != cur) {
+      if (first_run) {
+        part_keys[2 * tid] = cur;
+        acc.store(part_pts + 2 * tid);
+        first_run = false;
+      } else {
+        acc.store(buckets + cur);
+      }
+      acc = XYZZ<F>::infinity();
+      cur = key;
+    }
+    acc.add(XYZZ<F>::load(pts + i));
+  }
+  if (cur == kInvalidKey) return;
+  if (first_run) {
+    part_keys[2 * tid] = cur;
+    acc.store(part_pts + 2 * tid);
+  } else {
+    part_keys[2 * tid + 1] = cur;
+    acc.store(part_pts + 2 * tid + 1);
+  }
+}
+
+// ---------------------------------------------------------------- 5. finish
+// One thread per list entry; the thread that holds the first valid entry of a key sums the run.
+template <class F>
+__global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restrict__ keys,
+                                                         const XYZZ<F>* __restrict__ pts,
+                                                         uint32_t m, XYZZ<F>* __restrict__ buckets) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  uint32_t key = keys[i];
+  if (key == kInvalidKey) return;
+  for (uint32_t j = i; j > 0; j--) {     // previous valid entry with the same key -> not the head
+    uint32_t kp = keys[j - 1];
+    if (kp == kInvalidKey) continue;
+    if (kp == key) return;
+    break;
+  }
+  XYZZ<F> acc = XYZZ<F>::load(pts + i);
+  for (uint32_t j = i + 1; j < m; j++) {
+    uint32_t kn = keys[j];
+    if (kn == kInvalidKey) continue;
+    if (kn != key) break;
+    acc.add(XYZZ<F>::load(pts + j));
+  }
+  acc.store(buckets + key);
+}
+
+// ---------------------------------------------------------------- 6. bucket reduce
+// group of `gsize` consecutive buckets of one window -> sum_j (base + j + 1) * B_{base + j}
+template <class F>
+__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(
+    const XYZZ<F>* __restrict__ buckets, uint32_t half, uint32_t gsize, uint32_t groups_per_win,
+    uint32_t n_groups, XYZZ<F>* __restrict__ group_sums) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  uint32_t w = g / groups_per_win;
+  uint32_t gi = g - w * groups_per_win;
+  uint32_t base = gi * gsize;
+  const XYZZ<F>* b = buckets + uint64_t(w) * half + base;
+  XYZZ<F> run = XYZZ<F>::infinity(), wsum = XYZZ<F>::infinity();
+  for (int j = int(gsize) - 1; j >= 0; j--) {
+    run.add(XYZZ<F>::load(b + j));
+    wsum.add(run);
+  }
+  if (base) wsum.add(mul_small(run, base));
+  wsum.store(group_sums + g);
+}
+
+// ---------------------------------------------------------------- 7. window sum
+template <class F>
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __restrict__ group_sums,
+                                                             uint32_t groups_per_win,
+                                                             XYZZ<F>* __restrict__ window_sums) {
+  extern __shared__ uint4 sm_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sm_raw);
+  const uint32_t w = blockIdx.x, t = threadIdx.x;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  for (uint32_t g = t; g < groups_per_win; g += blockDim.x)
+    acc.add(XYZZ<F>::load(group_sums + uint64_t(w) * groups_per_win + g));
+  acc.store(sm + t);
+  __syncthreads();
+  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (t < s) {
+      XYZZ<F> a = XYZZ<F>::load(sm + t);
+      a.add(XYZZ<F>::load(sm + t + s));
+      a.store(sm + t);
+    }
+    __syncthreads();
+  }
+  if (t == 0) XYZZ<F>::load(sm).store(window_sums + w);
+}
+
+// ---------------------------------------------------------------- 8. Horner + output
+// result (Montgomery XYZZ, 4*sizeof(F) bytes) and canonical affine (2*sizeof(F) bytes)
+template <class F>
+__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ window_sums, uint32_t nwin,
+                                  uint32_t c, XYZZ<F>* __restrict__ out_xyzz,
+                                  Affine<F>* __restrict__ out_affine) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<F> acc = XYZZ<F>::load(window_sums + (nwin - 1));
+  for (int w = int(nwin) - 2; w >= 0; w--) {
+    for (uint32_t i = 0; i < c; i++) acc = acc.dbl();
+    acc.add(XYZZ<F>::load(window_sums + w));
+  }
+  acc.store(out_xyzz);
+  Affine<F> a = acc.to_affine();
+  a.x = a.x.from_mont();
+  a.y = a.y.from_mont();
+  a.store(out_affine);
+}
+
+// ---------------------------------------------------------------- base upload / point utilities
+// canonical affine -> Montgomery affine (infinity = all zero stays all zero)
+template <class F>
+__global__ void msm_bases_to_mont_kernel(Affine<F>* pts, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = Affine<F>::load(pts + i);
+  p.x = p.x.to_mont();
+  p.y = p.y.to_mont();
+  p.store(pts + i);
+}
+
+// sum of n canonical affine points (tiny n: partial results of the ranks) -> canonical affine
+template <class F>
+__global__ void msm_sum_affine_kernel(const Affine<F>* pts, uint32_t n, Affine<F>* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  for (uint32_t i = 0; i < n; i++) {
+    Affine<F> p = Affine<F>::load(pts + i);
+    p.x = p.x.to_mont();
+    p.y = p.y.to_mont();
+    acc.madd(p);
+  }
+  Affine<F> a = acc.to_affine();
+  a.x = a.x.from_mont();
+  a.y = a.y.from_mont();
+  a.store(out);
+}
+
+template <class F>
+void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                      const void* d_bases, cudaStream_t s) {
+  using P = XYZZ<F>;
+  msm_digits_and_sort(p, b, d_scalars, n, s);
+  cudaMemsetAsync(b.buckets, 0, p.n_buckets * sizeof(P), s);
+  msm_accumulate_l1_kernel<F><<<(p.l1_threads + 127) / 128, 128, 0, s>>>(
+      b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
+      reinterpret_cast<P*>(b.buckets), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
+      p.l1_threads);
+  msm_accumulate_l2_kernel<F><<<(p.l2_threads + 127) / 128, 128, 0, s>>>(
+      b.part1_keys, reinterpret_cast<const P*>(b.part1_pts), 2 * p.l1_threads, p.l2_len,
+      reinterpret_cast<P*>(b.buckets), b.part2_keys, reinterpret_cast<P*>(b.part2_pts),
+      p.l2_threads);
+  msm_finish_kernel<F><<<(2 * p.l2_threads + 127) / 128, 128, 0, s>>>(
+      b.part2_keys, reinterpret_cast<const P*>(b.part2_pts), 2 * p.l2_threads,
+      reinterpret_cast<P*>(b.buckets));
+  msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
+      reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
+      reinterpret_cast<P*>(b.group_sums));
+  msm_window_sum_kernel<F><<<p.nwin, 128, 128 * sizeof(P), s>>>(
+      reinterpret_cast<const P*>(b.group_sums), p.groups_per_win,
+      reinterpret_cast<P*>(b.window_sums));
+  msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.nwin, p.c,
+                                        reinterpret_cast<P*>(b.result_xyzz),
+                                        reinterpret_cast<Affine<F>*>(b.result_affine));
+}
+
+
+template <class F>
+void msm_bases_to_mont_t(void* d_pts, uint64_t n, cudaStream_t s) {
+  uint32_t blocks = uint32_t((n + 127) / 128);
+  if (blocks) msm_bases_to_mont_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<Affine<F>*>(d_pts), n);
+}
+template <class F>
+void msm_sum_affine_t(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s) {
+  msm_sum_affine_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const Affine<F>*>(d_pts), n,
+                                            reinterpret_cast<Affine<F>*>(d_out));
+}
+
+}  // namespace zkb

@@ -1,0 +1,39 @@
+// ntt.h — launch descriptors shared by ntt.cu (kernels) and the host planner in context.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace zkb {
+
+struct NttPassArgs {
+  const void* in;          // n x 32 B
+  void* out;               // n x 32 B (== in for the in-place column passes)
+  const void* stage_tw;    // 255 x 32 B dense per-stage twiddles (forward or inverse roots)
+  const void* tw_lo;       // two-level inter-pass twiddles  w_n^i, i < 2^tw_lo_bits
+  const void* tw_hi;       //                                w_n^{i * 2^tw_lo_bits}
+  const void* tw_full;     // optional full table for this pass (M entries), else nullptr
+  const void* pre_scale;   // optional n-entry table multiplied into the input (pass 0 only)
+  const void* post_scale;  // optional n-entry table multiplied into the output (last pass only)
+  uint64_t M;              // column mode: block size before this pass
+  uint32_t S;              // column mode: M >> k
+  uint32_t k;              // log2 of the sub-transform size of this pass (1..8)
+  uint32_t tw_shift;       // log2(n / M)
+  uint32_t tw_lo_bits;
+  uint64_t tw_lo_mask;
+  uint32_t row_bits;       // final mode: log2(number of rows) = log_n - k
+  uint32_t first_digit_bits;  // final mode: width of K_0 (0 when P == 1)
+  uint32_t n_row_digits;
+  uint32_t row_digit_bits[4];
+  int mont_in;             // 0: input is canonical integers, convert while loading
+  int mont_out;            // 0: convert the result back to canonical integers while storing
+};
+
+void ntt_launch_pass(const NttPassArgs& a, bool final, uint32_t tiles, cudaStream_t s);
+void fr_powers_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t count,
+                      uint64_t stride_pow, cudaStream_t s);
+void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t lo_bits,
+                            uint32_t tw_shift, uint32_t s_bits, uint64_t M, cudaStream_t s);
+void fr_convert_launch(void* data, uint64_t n, int to_mont, cudaStream_t s);
+
+}  // namespace zkb

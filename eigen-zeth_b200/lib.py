@@ -1,0 +1,289 @@
+"""ctypes binding of libzkb.so (include/zkb.h) — the host-side mirror of the C ABI.
+
+There is NO CPU fallback: if the shared library is missing, or no sm_100 GPU is present,
+every compute entry point raises.  Byte layouts are those of include/zkb.h (canonical
+little-endian field elements; proof.json coordinate order of reference proof/proof.json).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb.so")
+
+ZKB_OK, ZKB_EINVAL, ZKB_ECUDA, ZKB_ENOMEM, ZKB_EBUSY, ZKB_ENOGPU, ZKB_EVERIFY = 0, -1, -2, -3, -4, -5, -6
+VK_BYTES, PROOF_BYTES, INTERMEDIATE_BYTES = 576, 256, 384
+
+EXPORTS = [
+    "zkb_version", "zkb_ctx_create", "zkb_ctx_destroy", "zkb_last_error", "zkb_ctx_stream", "zkb_ctx_sync",
+    "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
+    "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
+    "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
+    "zkb_pk_synthetic", "zkb_pk_free", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe",
+]
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("zkb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ProveTimings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_spmv", "ms_ntt", "ms_msm_a", "ms_msm_b1", "ms_msm_b2",
+                                         "ms_msm_l", "ms_msm_h", "ms_total")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libzkb.so and declare prototypes; raises if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libzkb.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                          "there is no CPU fallback for the proving path")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, u64, u32, i32 = C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_int
+    lib.zkb_version.restype = C.c_char_p
+    lib.zkb_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.zkb_ctx_destroy.argtypes = [vp]
+    lib.zkb_ctx_destroy.restype = None
+    lib.zkb_last_error.argtypes = [vp]
+    lib.zkb_last_error.restype = C.c_char_p
+    lib.zkb_ctx_stream.argtypes = [vp]
+    lib.zkb_ctx_stream.restype = vp
+    lib.zkb_ctx_sync.argtypes = [vp]
+    lib.zkb_ctx_set.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.zkb_fr_ntt.argtypes = [vp, vp, u32, i32, i32]
+    lib.zkb_fr_ntt_dev.argtypes = [vp, vp, vp, u32, i32, i32, i32]
+    for g in ("g1", "g2"):
+        getattr(lib, "zkb_bases_upload_" + g).argtypes = [vp, u8p, u64, C.POINTER(vp)]
+        getattr(lib, "zkb_bases_synthetic_" + g).argtypes = [vp, u64, u64, C.POINTER(vp)]
+        getattr(lib, "zkb_msm_" + g).argtypes = [vp, vp, u64, vp, u64, vp]
+        getattr(lib, "zkb_msm_" + g + "_dev").argtypes = [vp, vp, u64, vp, u64, vp]
+        getattr(lib, "zkb_" + g + "_sum").argtypes = [vp, u8p, u32, vp]
+    lib.zkb_bases_download.argtypes = [vp, vp, u64, u64, vp]
+    lib.zkb_bases_len.argtypes = [vp]
+    lib.zkb_bases_len.restype = u64
+    lib.zkb_bases_free.argtypes = [vp]
+    lib.zkb_bases_free.restype = None
+    if hasattr(lib, "zkb_pk_synthetic"):
+        lib.zkb_pk_synthetic.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
+        lib.zkb_pk_free.argtypes = [vp]
+        lib.zkb_pk_free.restype = None
+        lib.zkb_synthetic_witness.argtypes = [u32, u8p, u8p, vp]
+        lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
+        lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
+    lib.zkb_field_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
+    lib.zkb_curve_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
+    lib.zkb_bench_int_pipe.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def version() -> str:
+    return load_library().zkb_version().decode()
+
+
+class Bases:
+    """device-resident MSM bases (affine, Montgomery form on the GPU)."""
+
+    def __init__(self, ctx: "Context", handle, g2: bool):
+        self.ctx, self.handle, self.g2 = ctx, handle, g2
+
+    def __len__(self):
+        return int(self.ctx.lib.zkb_bases_len(self.handle))
+
+    def download(self, first=0, count=None) -> bytes:
+        count = len(self) - first if count is None else count
+        buf = C.create_string_buffer(count * (128 if self.g2 else 64))
+        self.ctx._check(self.ctx.lib.zkb_bases_download(self.ctx.h, self.handle, first, count, buf))
+        return buf.raw
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zkb_bases_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ProvingKey:
+    def __init__(self, ctx, handle, vk: bytes, log_n: int):
+        self.ctx, self.handle, self.vk, self.log_n = ctx, handle, vk, log_n
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zkb_pk_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """one GPU, one stream; not re-entrant (ZKB_EBUSY)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.zkb_ctx_create(device, C.byref(h))
+        if rc == ZKB_ENOGPU:
+            raise ZkbError(rc, "no sm_100 GPU visible; the proving path has no CPU fallback")
+        if rc:
+            raise ZkbError(rc, "zkb_ctx_create failed")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zkb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise ZkbError(rc, self.lib.zkb_last_error(self.h).decode(errors="replace"))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.zkb_ctx_stream(self.h) or 0)
+
+    def sync(self):
+        self._check(self.lib.zkb_ctx_sync(self.h))
+
+    def set(self, key: str, value: int):
+        self._check(self.lib.zkb_ctx_set(self.h, key.encode(), value))
+
+    # ---- NTT
+    def fr_ntt(self, data: bytes, inverse=False, coset=False) -> bytes:
+        n = len(data) // 32
+        if n * 32 != len(data) or n & (n - 1) or n < 2:
+            raise ValueError("length must be 32 * 2^k, k >= 1")
+        buf = C.create_string_buffer(bytes(data), len(data))
+        self._check(self.lib.zkb_fr_ntt(self.h, buf, n.bit_length() - 1, int(inverse), int(coset)))
+        return buf.raw
+
+    def fr_ntt_dev(self, d_in: int, d_out: int, log_n: int, inverse=False, coset=False, montgomery=False):
+        self._check(self.lib.zkb_fr_ntt_dev(self.h, d_in, d_out, log_n, int(inverse), int(coset), int(montgomery)))
+
+    # ---- bases / MSM
+    def upload_bases(self, affine: bytes, g2=False) -> Bases:
+        sz = 128 if g2 else 64
+        n = len(affine) // sz
+        h = C.c_void_p()
+        fn = self.lib.zkb_bases_upload_g2 if g2 else self.lib.zkb_bases_upload_g1
+        self._check(fn(self.h, bytes(affine), n, C.byref(h)))
+        return Bases(self, h, g2)
+
+    def synthetic_bases(self, n: int, seed: int, g2=False) -> Bases:
+        h = C.c_void_p()
+        fn = self.lib.zkb_bases_synthetic_g2 if g2 else self.lib.zkb_bases_synthetic_g1
+        self._check(fn(self.h, n, seed, C.byref(h)))
+        return Bases(self, h, g2)
+
+    def msm(self, bases: Bases, scalars: bytes, first=0) -> bytes:
+        n = len(scalars) // 32
+        out = C.create_string_buffer(128 if bases.g2 else 64)
+        fn = self.lib.zkb_msm_g2 if bases.g2 else self.lib.zkb_msm_g1
+        sbuf = C.create_string_buffer(bytes(scalars), max(len(scalars), 1))
+        self._check(fn(self.h, bases.handle, first, sbuf, n, out))
+        return out.raw
+
+    def msm_raw(self, bases: Bases, host_ptr: int, n: int, first=0) -> bytes:
+        """scalars given as a raw host pointer (e.g. pinned torch tensor .data_ptr())."""
+        out = C.create_string_buffer(128 if bases.g2 else 64)
+        fn = self.lib.zkb_msm_g2 if bases.g2 else self.lib.zkb_msm_g1
+        self._check(fn(self.h, bases.handle, first, host_ptr, n, out))
+        return out.raw
+
+    def msm_dev(self, bases: Bases, d_scalars: int, n: int, d_out: int, first=0):
+        fn = self.lib.zkb_msm_g2_dev if bases.g2 else self.lib.zkb_msm_g1_dev
+        self._check(fn(self.h, bases.handle, first, d_scalars, n, d_out))
+
+    def point_sum(self, points: bytes, g2=False) -> bytes:
+        sz = 128 if g2 else 64
+        out = C.create_string_buffer(sz)
+        fn = self.lib.zkb_g2_sum if g2 else self.lib.zkb_g1_sum
+        self._check(fn(self.h, bytes(points), len(points) // sz, out))
+        return out.raw
+
+    # ---- Groth16
+    def pk_synthetic(self, log_n: int, seed: int) -> ProvingKey:
+        h = C.c_void_p()
+        vk = C.create_string_buffer(VK_BYTES)
+        self._check(self.lib.zkb_pk_synthetic(self.h, log_n, seed, C.byref(h), vk))
+        return ProvingKey(self, h, vk.raw, log_n)
+
+    def groth16_prove(self, pk: ProvingKey, witness, r: bytes, s: bytes, want_intermediates=False, want_h=False):
+        """witness: bytes or raw host pointer (int). returns (proof, intermediates|None, h|None, timings)."""
+        proof = C.create_string_buffer(PROOF_BYTES)
+        inter = C.create_string_buffer(INTERMEDIATE_BYTES) if want_intermediates else None
+        hbuf = C.create_string_buffer(32 * ((1 << pk.log_n) - 1)) if want_h else None
+        t = ProveTimings()
+        if isinstance(witness, (bytes, bytearray)):
+            wbuf = C.create_string_buffer(bytes(witness), len(witness))
+            wptr = C.cast(wbuf, C.c_void_p)
+        else:
+            wptr = C.c_void_p(int(witness))
+        self._check(self.lib.zkb_groth16_prove(self.h, pk.handle, wptr, r, s, proof, inter, hbuf, C.byref(t)))
+        return proof.raw, (inter.raw if inter else None), (hbuf.raw if hbuf else None), t.as_dict()
+
+    # ---- hooks
+    def field_op(self, field: int, op: int, a: bytes, b: bytes | None = None) -> bytes:
+        n = len(a) // 32
+        out = C.create_string_buffer(max(len(a), 1))
+        self._check(self.lib.zkb_field_batch_op(self.h, field, op, bytes(a), bytes(b) if b is not None else None, out, n))
+        return out.raw[: len(a)]
+
+    def curve_op(self, group: int, op: int, a: bytes, b: bytes | None = None) -> bytes:
+        sz = 128 if group else 64
+        n = len(a) // sz
+        out = C.create_string_buffer(max(len(a), 1))
+        self._check(self.lib.zkb_curve_batch_op(self.h, group, op, bytes(a), bytes(b) if b is not None else None, out, n))
+        return out.raw[: len(a)]
+
+    def bench_int_pipe(self, iters=2000):
+        res = (C.c_double * 3)()
+        self._check(self.lib.zkb_bench_int_pipe(self.h, iters, res))
+        return {"imad_wide_per_s": res[0], "montmul_per_s": res[1], "sm_mhz": res[2]}
+
+
+def synthetic_witness(log_n: int, w0: bytes, w1: bytes) -> bytes:
+    lib = load_library()
+    out = C.create_string_buffer(32 << log_n)
+    rc = lib.zkb_synthetic_witness(log_n, w0, w1, out)
+    if rc:
+        raise ZkbError(rc, "zkb_synthetic_witness failed")
+    return out.raw
+
+
+def groth16_verify(vk: bytes, proof: bytes, public_input: bytes) -> bool:
+    """CPU pairing check; False for an invalid proof, raises for a malformed one."""
+    lib = load_library()
+    rc = lib.zkb_groth16_verify(vk, proof, public_input)
+    if rc == ZKB_OK:
+        return True
+    if rc == ZKB_EVERIFY:
+        return False
+    raise ZkbError(rc, "malformed verifying key / proof / input")

@@ -1,0 +1,132 @@
+/* zkb.h — C ABI of libzkb.so, the B200-native BN254 Groth16 proving backend.
+ *
+ * This is the drop-in boundary UNDER eigen-zeth's prover service: the reference reaches its
+ * prover only over gRPC (reference proto/prover/v1/prover.proto:9-11, client at
+ * src/prover/provider.rs:603-705) and has no FFI of its own, so each entry point
+ * below cites the piece of the reference-side contract it serves rather than a function it
+ * replaces.  A Rust `-sys` crate binds these symbols 1:1 through build.rs.
+ *
+ * Conventions
+ *  - every function returns 0 (ZKB_OK) or a negative error code; zkb_last_error(ctx) explains;
+ *  - no exception or abort crosses this boundary;
+ *  - field elements: 32 bytes, little-endian, canonical (< modulus), NOT Montgomery;
+ *  - G1 affine: x||y (64 B); G2 affine: x.c0||x.c1||y.c0||y.c1 (128 B); all-zero = infinity.
+ *    (c0 first is the order of reference proof/proof.json "pi_b", read unswapped by
+ *     src/settlement/ethereum/mod.rs:451-466.)
+ *  - a zkb_ctx is bound to ONE GPU (one process per GPU; ranks are composed above this layer
+ *    with NCCL) and is not re-entrant: one call at a time per ctx (ZKB_EBUSY otherwise);
+ *  - `*_dev` variants take raw device pointers on the ctx's device and enqueue on the ctx's
+ *    stream (zkb_ctx_stream) without synchronising, so callers can time them with CUDA events.
+ */
+#ifndef ZKB_H
+#define ZKB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+#define ZKB_OK 0
+#define ZKB_EINVAL (-1)   /* bad argument (size, non-canonical field element, null pointer) */
+#define ZKB_ECUDA (-2)    /* CUDA runtime error (message in zkb_last_error) */
+#define ZKB_ENOMEM (-3)
+#define ZKB_EBUSY (-4)    /* ctx already executing a call on another thread */
+#define ZKB_ENOGPU (-5)   /* no usable sm_100 device: there is no CPU fallback */
+#define ZKB_EVERIFY (-6)  /* pairing check failed */
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_bases zkb_bases;
+typedef struct zkb_pk zkb_pk;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int zkb_ctx_create(int device, zkb_ctx** out);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(const zkb_ctx* ctx);
+void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
+int zkb_ctx_sync(zkb_ctx* ctx);
+/* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1) */
+int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
+const char* zkb_version(void);
+
+/* ---- Fr NTT  (serves the 7 transforms of GenFinalProof) ---------------- */
+/* in place on a host buffer of 2^log_n canonical elements; ark-poly Radix2EvaluationDomain
+ * semantics: natural order, inverse carries 1/n, coset uses the shift g = 5. */
+int zkb_fr_ntt(zkb_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, int coset);
+/* device-resident variant: d_in -> d_out (may alias), elements canonical unless montgomery != 0 */
+int zkb_fr_ntt_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
+                   int coset, int montgomery);
+
+/* ---- MSM  (serves the A/B1/L/H G1 MSMs and the B2 G2 MSM) ---------- */
+int zkb_bases_upload_g1(zkb_ctx* ctx, const uint8_t* affine, uint64_t n, zkb_bases** out);
+int zkb_bases_upload_g2(zkb_ctx* ctx, const uint8_t* affine, uint64_t n, zkb_bases** out);
+/* deterministic synthetic bases P_i = k_i * G (k_i from xoshiro256**(seed)), generated on the GPU */
+int zkb_bases_synthetic_g1(zkb_ctx* ctx, uint64_t n, uint64_t seed, zkb_bases** out);
+int zkb_bases_synthetic_g2(zkb_ctx* ctx, uint64_t n, uint64_t seed, zkb_bases** out);
+/* copy `count` bases starting at `first` back to the host in canonical form */
+int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
+                       uint8_t* out);
+uint64_t zkb_bases_len(const zkb_bases* b);
+void zkb_bases_free(zkb_bases* b);
+/* sum_i scalars[i] * bases[first + i], i < n; host scalars; result canonical affine (64 / 128 B) */
+int zkb_msm_g1(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,
+               uint64_t n, uint8_t out[64]);
+int zkb_msm_g2(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,
+               uint64_t n, uint8_t out[128]);
+/* device-resident scalars (canonical); d_out is a device buffer of 64 / 128 bytes; asynchronous */
+int zkb_msm_g1_dev(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars,
+                   uint64_t n, void* d_out);
+int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars,
+                   uint64_t n, void* d_out);
+/* sum of n affine points (the per-rank partial results of a point-range-sharded MSM) */
+int zkb_g1_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[64]);
+int zkb_g2_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[128]);
+
+/* ---- Groth16  (GenFinalProofRequest -> FinalProof; prover.proto:130-148) --------------------- */
+/* verifying key layout: alpha_g1 64 | beta_g2 128 | gamma_g2 128 | delta_g2 128 | ic0 64 | ic1 64 */
+#define ZKB_VK_BYTES 576
+#define ZKB_PROOF_BYTES 256 /* A 64 | B 128 | C 64 */
+/* synthetic chain circuit with 2^log_n - 2 constraints, 2^log_n variables, 1 public input;
+ * toxic waste from xoshiro256**(seed); queries are computed on the GPU and stay resident. */
+int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
+                     uint8_t vk_out[ZKB_VK_BYTES]);
+void zkb_pk_free(zkb_pk* pk);
+/* full witness assignment z (2^log_n canonical Fr, z[0] = 1, z[1] = public input) from two seeds */
+int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
+                          uint8_t* z_out);
+typedef struct zkb_prove_timings {
+  float ms_h2d, ms_spmv, ms_ntt, ms_msm_a, ms_msm_b1, ms_msm_b2, ms_msm_l, ms_msm_h, ms_total;
+} zkb_prove_timings;
+/* intermediates (optional, may be NULL): msm_a 64 | msm_b1 64 | msm_b2 128 | msm_l 64 | msm_h 64 */
+#define ZKB_INTERMEDIATE_BYTES 384
+int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
+                      const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
+                      uint8_t* intermediates_opt, uint8_t* h_out_opt,
+                      zkb_prove_timings* timings_opt);
+/* CPU pairing check e(A,B) = e(alpha,beta) e(ic0 + x*ic1, gamma) e(C,delta); 0 = valid,
+ * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
+int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],
+                       const uint8_t public_input[32]);
+
+/* ---- test / measurement hooks ------------------------------------------------------------------ */
+/* element-wise field ops on host arrays of canonical elements, executed by the device field
+ * library: field 0 = Fq, 1 = Fr; op 0 add, 1 sub, 2 mul, 3 sqr, 4 inverse, 5 neg */
+int zkb_field_batch_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
+                       uint8_t* out, uint64_t n);
+/* curve ops through the device XYZZ library: group 0 = G1, 1 = G2;
+ * op 0: out[i] = a[i] + b[i]   (b = affine points)
+ * op 1: out[i] = 2 a[i]
+ * op 2: out[i] = k[i] * a[i]   (b = 32-byte scalars) */
+int zkb_curve_batch_op(zkb_ctx* ctx, int group, int op, const uint8_t* a, const uint8_t* b,
+                       uint8_t* out, uint64_t n);
+/* integer-pipe microbenchmark: results[0] = IMAD.WIDE.U32 carry-chain ops/s,
+ * results[1] = Montgomery multiplications/s (register resident), results[2] = SM clock (MHz)
+ * measured over the run with clock64 */
+int zkb_bench_int_pipe(zkb_ctx* ctx, int iters, double results[3]);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB_H */

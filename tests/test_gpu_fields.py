@@ -1,0 +1,66 @@
+"""K1-K3 parity: device Montgomery field library and XYZZ curve ops vs Python big ints (oracle A)."""
+import pytest
+
+import oracle_a as o
+from helpers import fr_bytes, fr_list, g1_bytes, g1_list, g2_bytes, g2_list, rand_fq, rand_fr
+
+pytestmark = pytest.mark.gpu
+
+OPS = {0: lambda a, b, p: (a + b) % p, 1: lambda a, b, p: (a - b) % p, 2: lambda a, b, p: a * b % p,
+       3: lambda a, b, p: a * a % p, 4: lambda a, b, p: pow(a, p - 2, p), 5: lambda a, b, p: (-a) % p}
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_ops_bit_exact(ctx, field):
+    p = o.Q if field == 0 else o.R
+    rng = o.Xoshiro256ss(100 + field)
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 256) % p, (p + 1) // 2, (1 << 253), (1 << 32) - 1, (1 << 64), p >> 1]
+    rnd = rand_fq(rng, 2000) if field == 0 else rand_fr(rng, 2000)
+    a = edge + rnd + [x for x in edge for _ in edge]
+    b = edge[::-1] + rnd[::-1] + [y for _ in edge for y in edge]
+    assert len(a) == len(b)
+    for op, f in OPS.items():
+        got = fr_list(ctx.field_op(field, op, fr_bytes(a), fr_bytes(b)))
+        want = [f(x, y, p) for x, y in zip(a, b)]
+        assert got == want, "field %d op %d" % (field, op)
+
+
+def test_field_rejects_nothing_silently(ctx, zkb):
+    # a non-canonical scalar must be rejected at the ABI (error behaviour mirrors U256 range checks)
+    bases = ctx.upload_bases(g1_bytes([o.G1_GEN]))
+    with pytest.raises(zkb.ZkbError):
+        ctx.msm(bases, int(o.R).to_bytes(32, "little"))
+    with pytest.raises(zkb.ZkbError):
+        ctx.upload_bases(int(o.Q).to_bytes(32, "little") + bytes(32))
+
+
+def test_g1_ops(ctx):
+    rng = o.Xoshiro256ss(7)
+    ks = [rng.fr() for _ in range(24)]
+    P = [o.g1_mul(o.G1_GEN, k) for k in ks]
+    S = P[1:] + P[:1]
+    # generic add, doubling (P+P), cancellation (P + -P), infinity operands
+    a = P + P[:4] + P[:4] + [None, P[0], None]
+    b = S + P[:4] + [o.g1_neg(x) for x in P[:4]] + [P[1], None, None]
+    got = g1_list(ctx.curve_op(0, 0, g1_bytes(a), g1_bytes(b)))
+    assert got == [o.g1_add(x, y) for x, y in zip(a, b)]
+    got = g1_list(ctx.curve_op(0, 1, g1_bytes(P + [None])))
+    assert got == [o.g1_add(x, x) for x in P] + [None]
+    sc = [0, 1, 2, o.R - 1, o.R - 2] + [rng.fr() for _ in range(11)]
+    got = g1_list(ctx.curve_op(0, 2, g1_bytes(P[:16]), fr_bytes(sc)))
+    assert got == [o.g1_mul(x, k) for x, k in zip(P[:16], sc)]
+
+
+def test_g2_ops(ctx):
+    rng = o.Xoshiro256ss(8)
+    P = [o.g2_mul(o.G2_GEN, rng.fr()) for _ in range(10)]
+    S = P[1:] + P[:1]
+    a = P + P[:3] + P[:3] + [None, P[0]]
+    b = S + P[:3] + [o.g2_neg(x) for x in P[:3]] + [P[1], None]
+    got = g2_list(ctx.curve_op(1, 0, g2_bytes(a), g2_bytes(b)))
+    assert got == [o.g2_add(x, y) for x, y in zip(a, b)]
+    got = g2_list(ctx.curve_op(1, 1, g2_bytes(P)))
+    assert got == [o.g2_add(x, x) for x in P]
+    sc = [0, 1, o.R - 1] + [rng.fr() for _ in range(5)]
+    got = g2_list(ctx.curve_op(1, 2, g2_bytes(P[:8]), fr_bytes(sc)))
+    assert got == [o.g2_mul(x, k) for x, k in zip(P[:8], sc)]

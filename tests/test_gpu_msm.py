@@ -1,0 +1,119 @@
+"""K4-K8 parity: GPU Pippenger MSM (G1, G2) vs oracle A on small sizes + algebraic properties."""
+import pytest
+
+import oracle_a as o
+from helpers import fr_bytes, g1_bytes, g1_list, g2_bytes, g2_list, rand_fr
+
+pytestmark = pytest.mark.gpu
+
+
+def _g1_points(rng, n):
+    """n distinct points cheaply: running sums of a few random multiples of G."""
+    base = [o.g1_mul(o.G1_GEN, rng.fr()) for _ in range(4)]
+    pts, acc = [], base[0]
+    for i in range(n):
+        acc = o.g1_add(acc, base[i & 3])
+        pts.append(acc)
+    return pts
+
+
+def _g2_points(rng, n):
+    base = [o.g2_mul(o.G2_GEN, rng.fr()) for _ in range(4)]
+    pts, acc = [], base[0]
+    for i in range(n):
+        acc = o.g2_add(acc, base[i & 3])
+        pts.append(acc)
+    return pts
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 300])
+@pytest.mark.parametrize("window", [0, 2, 5, 13, 16])
+def test_msm_g1_matches_oracle(ctx, n, window):
+    rng = o.Xoshiro256ss(n * 31 + window)
+    pts = _g1_points(rng, n)
+    sc = rand_fr(rng, n)
+    ctx.set("msm_window", window)
+    try:
+        bases = ctx.upload_bases(g1_bytes(pts))
+        got = o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc)))
+    finally:
+        ctx.set("msm_window", 0)
+    assert got == o.msm_g1(pts, sc)
+
+
+def test_msm_g1_edge_scalars(ctx):
+    rng = o.Xoshiro256ss(5)
+    n = 200
+    pts = _g1_points(rng, n)
+    pts[3] = None                       # infinity base
+    pts[10] = pts[11]                   # equal bases in one bucket (doubling path)
+    pts[20] = o.g1_neg(pts[21])         # P and -P in one bucket (cancellation path)
+    bases = ctx.upload_bases(g1_bytes(pts))
+    cases = {
+        "zero": [0] * n,
+        "one": [1] * n,
+        "r-1": [o.R - 1] * n,
+        "half_digits": [sum((1 << 15) << (16 * w) for w in range(15))] * n,
+        "sparse": [rng.fr() if i % 2 else 0 for i in range(n)],
+        "bits": [i & 1 for i in range(n)],
+        "same": [rng.fr()] * n,
+    }
+    for name, sc in cases.items():
+        sc = [s % o.R for s in sc]
+        for w in (0, 16):
+            ctx.set("msm_window", w)
+            got = o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc)))
+            ctx.set("msm_window", 0)
+            assert got == o.msm_g1(pts, sc), (name, w)
+    assert ctx.msm(bases, b"") == bytes(64)
+
+
+@pytest.mark.parametrize("n", [1, 5, 130])
+def test_msm_g2_matches_oracle(ctx, n):
+    rng = o.Xoshiro256ss(n + 1000)
+    pts = _g2_points(rng, n)
+    if n > 4:
+        pts[2] = None
+        pts[3] = pts[4]
+    sc = rand_fr(rng, n)
+    sc[0] = o.R - 1
+    bases = ctx.upload_bases(g2_bytes(pts), g2=True)
+    assert o.g2_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g2(pts, sc)
+
+
+def test_synthetic_bases_and_large_properties(ctx):
+    """bases P_i = k_i G are generated on the GPU; spot-check them, then use the closed form
+    sum s_i P_i = (sum s_i k_i) G to check a 2^18 MSM without a big CPU computation."""
+    n, seed = 1 << 18, 0x5EED0001
+    bases = ctx.synthetic_bases(n, seed)
+    rng = o.Xoshiro256ss(seed)
+    ks = [rng.fr() for _ in range(n)]
+    head = g1_list(bases.download(0, 8))
+    assert head == [o.g1_mul(o.G1_GEN, k) for k in ks[:8]]
+    tail = g1_list(bases.download(n - 4, 4))
+    assert tail == [o.g1_mul(o.G1_GEN, k) for k in ks[-4:]]
+    srng = o.Xoshiro256ss(0x5EED0000 + 18)
+    sc = [srng.fr() for _ in range(n)]
+    want = o.g1_mul(o.G1_GEN, sum(s * k for s, k in zip(sc, ks)) % o.R)
+    assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc))) == want
+    # skewed: witness-like 0/1 scalars and all-equal scalars (one giant bucket)
+    sc01 = [(i * 7) & 1 for i in range(n)]
+    want = o.g1_mul(o.G1_GEN, sum(k for s, k in zip(sc01, ks) if s) % o.R)
+    assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc01))) == want
+    want = o.g1_mul(o.G1_GEN, 12345 * sum(ks) % o.R)
+    assert o.g1_from_bytes(ctx.msm(bases, fr_bytes([12345] * n))) == want
+    # sub-range + linearity: MSM over [a, b) pieces sums to the whole
+    parts = [ctx.msm(bases, fr_bytes(sc[a:a + n // 4]), first=a) for a in range(0, n, n // 4)]
+    assert ctx.point_sum(b"".join(parts)) == ctx.msm(bases, fr_bytes(sc))
+
+
+def test_synthetic_g2_closed_form(ctx):
+    n, seed = 1 << 12, 0x5EED0002
+    bases = ctx.synthetic_bases(n, seed, g2=True)
+    rng = o.Xoshiro256ss(seed)
+    ks = [rng.fr() for _ in range(n)]
+    assert g2_list(bases.download(0, 2)) == [o.g2_mul(o.G2_GEN, k) for k in ks[:2]]
+    srng = o.Xoshiro256ss(99)
+    sc = [srng.fr() for _ in range(n)]
+    want = o.g2_mul(o.G2_GEN, sum(s * k for s, k in zip(sc, ks)) % o.R)
+    assert o.g2_from_bytes(ctx.msm(bases, fr_bytes(sc))) == want
