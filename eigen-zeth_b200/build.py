@@ -6,6 +6,7 @@ library in eigen-zeth_b200/libzkb.so (git-ignored, but it travels with the gpuru
 from __future__ import annotations
 
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -29,12 +30,20 @@ def _sources():
     return out
 
 
-def _headers_mtime():
-    m = 0.0
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            if f.endswith((".h", ".hpp", ".cuh")):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps_mtime(path, seen=None):
+    """newest mtime of `path` and of everything it #includes with quotes (recursively)."""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return 0.0
+    seen.add(path)
+    m = os.path.getmtime(path)
+    with open(path) as f:
+        for inc in _INC.findall(f.read()):
+            m = max(m, _deps_mtime(os.path.join(os.path.dirname(path), inc), seen))
     return m
 
 
@@ -51,12 +60,11 @@ def _compile(src, obj):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    hm = _headers_mtime()
     jobs, objs = [], []
     for src in _sources():
         obj = os.path.join(BUILD, os.path.basename(src) + ".o")
         objs.append(obj)
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hm):
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < _deps_mtime(src):
             jobs.append((src, obj))
     if jobs:
         if verbose:

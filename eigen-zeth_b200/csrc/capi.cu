@@ -420,6 +420,25 @@ int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g
   return ZKB_OK;
 }
 
+int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
+                          uint8_t* out) {
+  if (!b || !out || first > b->n || count > b->n - first) return set_error(ctx, ZKB_EINVAL, "bad range");
+  if (!count) return ZKB_OK;
+  const size_t sz = b->is_g2 ? 128 : 64;
+  ZKB_CUDA(ctx, ctx->io_b.ensure(count * sz));
+  uint32_t blocks = uint32_t((count + 127) / 128);
+  const char* src = reinterpret_cast<const char*>(b->d_pts) + first * sz;
+  if (b->is_g2)
+    bases_from_mont_kernel<Fq2><<<blocks, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const Affine<Fq2>*>(src), reinterpret_cast<Affine<Fq2>*>(ctx->io_b.p), count);
+  else
+    bases_from_mont_kernel<Fq><<<blocks, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const Affine<Fq>*>(src), reinterpret_cast<Affine<Fq>*>(ctx->io_b.p), count);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, count * sz, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
 // ---------------------------------------------------------------- integer-pipe microbenchmark
 // 8 independent 2-instruction carry chains per thread, ILP high enough to saturate the pipe.
 __global__ void __launch_bounds__(256) imad_chain_kernel(uint32_t* sink, int iters, uint32_t seed,
@@ -680,21 +699,7 @@ int zkb_bases_synthetic_g2(zkb_ctx* ctx, uint64_t n, uint64_t seed, zkb_bases** 
 int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
                        uint8_t* out) {
   ZKB_ENTER(ctx);
-  if (!b || !out || first > b->n || count > b->n - first) return set_error(ctx, ZKB_EINVAL, "bad range");
-  if (!count) return ZKB_OK;
-  const size_t sz = b->is_g2 ? 128 : 64;
-  ZKB_CUDA(ctx, ctx->io_b.ensure(count * sz));
-  uint32_t blocks = uint32_t((count + 127) / 128);
-  const char* src = reinterpret_cast<const char*>(b->d_pts) + first * sz;
-  if (b->is_g2)
-    bases_from_mont_kernel<Fq2><<<blocks, 128, 0, ctx->stream>>>(
-        reinterpret_cast<const Affine<Fq2>*>(src), reinterpret_cast<Affine<Fq2>*>(ctx->io_b.p), count);
-  else
-    bases_from_mont_kernel<Fq><<<blocks, 128, 0, ctx->stream>>>(
-        reinterpret_cast<const Affine<Fq>*>(src), reinterpret_cast<Affine<Fq>*>(ctx->io_b.p), count);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, count * sz, cudaMemcpyDeviceToHost, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
+  return bases_download_nolock(ctx, b, first, count, out);
 }
 
 uint64_t zkb_bases_len(const zkb_bases* b) { return b ? b->n : 0; }

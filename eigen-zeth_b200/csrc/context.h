@@ -110,6 +110,8 @@ int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out);
 int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
              void* d_out_affine);
 int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g2, void* d_out);
+int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
+                          uint8_t* out);
 
 void host_fr_root(uint32_t log_n, int inverse, uint32_t out_mont[8]);
 

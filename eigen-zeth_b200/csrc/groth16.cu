@@ -1,0 +1,527 @@
+// groth16.cu — the Groth16 prover pipeline on one B200: R1CS matrix-vector products, the 7 NTTs
+// of the QAP witness map, the five MSMs and proof assembly; plus synthetic proving-key generation.
+//
+// This is the device-side body of GenFinalProof (reference proto/prover/v1/prover.proto:130-148,
+// requested from src/prover/provider.rs:472-483).  The algorithm is ark-groth16's
+// create_proof_with_reduction_and_matrices with the LibsnarkReduction witness map (SURVEY.md
+// Appendix B): domain = 2^log_n >= #constraints + #instance, coefficient-form H, coset shift 5.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "context.h"
+#include "ec.cuh"
+
+using namespace zkb;
+using zkb::host::HFr;
+
+struct zkb_pk {
+  int device = 0;
+  uint32_t log_n = 0;
+  uint64_t n = 0, m = 0, ncons = 0;
+  zkb_bases *a_query = nullptr, *b_g1_query = nullptr, *b_g2_query = nullptr, *l_query = nullptr,
+            *h_query = nullptr;
+  // fixed points, affine Montgomery, device: alpha_g1 | beta_g1 | delta_g1 (3 x 64 B) and
+  // beta_g2 | delta_g2 (2 x 128 B)
+  void* d_fixed = nullptr;
+  // CSR matrices A, B, C (device)
+  uint32_t* d_row_ptr[3] = {nullptr, nullptr, nullptr};
+  uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
+  uint32_t* d_cidx[3] = {nullptr, nullptr, nullptr};
+  void* d_coeff_table = nullptr;     // Fr Montgomery
+  // work vectors (device, n x 32 B each) and witness staging
+  void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_z = nullptr, *d_zm = nullptr;
+  void* d_results = nullptr;         // msm_a 64 | msm_b1 64 | msm_b2 128 | msm_l 64 | msm_h 64
+  void* d_proof = nullptr;           // 256 B + r,s staging (64 B)
+};
+
+namespace zkb {
+
+// ---------------------------------------------------------------- kernels
+__global__ void fr_to_mont_copy_kernel(const Fr* in, Fr* out, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  Fr::load(in + i).to_mont().store(out + i);
+}
+
+// out[j] = sum_k coeff[cidx[k]] * z[col[k]] over row j of a CSR matrix; rows >= nrows: see below
+__global__ void r1cs_spmv_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                                 const uint32_t* __restrict__ cidx, const Fr* __restrict__ coeffs,
+                                 const Fr* __restrict__ z, Fr* __restrict__ out, uint64_t nrows,
+                                 uint64_t n, int copy_instance, uint32_t n_instance) {
+  uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  Fr acc = Fr::zero();
+  if (j < nrows) {
+    uint32_t lo = row_ptr[j], hi = row_ptr[j + 1];
+    for (uint32_t k = lo; k < hi; k++) {
+      Fr c = Fr::load_nc(coeffs + cidx[k]);
+      Fr v = Fr::load_nc(z + col[k]);
+      acc = acc + c * v;
+    }
+  } else if (copy_instance && j - nrows < n_instance) {
+    acc = Fr::load_nc(z + (j - nrows));   // ark-groth16 input-consistency rows of A
+  }
+  acc.store(out + j);
+}
+
+// a[i] = a[i] * b[i] - c[i]    (the 1/Z(g) factor is folded into the last coset-iNTT table)
+__global__ void qap_pointwise_kernel(Fr* a, const Fr* b, const Fr* c, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  (Fr::load(a + i) * Fr::load(b + i) - Fr::load(c + i)).store(a + i);
+}
+
+template <class F>
+__device__ Affine<F> load_canonical_affine(const void* p) {
+  Affine<F> a = Affine<F>::load(p);
+  a.x = a.x.to_mont();
+  a.y = a.y.to_mont();
+  return a;
+}
+template <class F>
+__device__ void store_canonical_affine(const XYZZ<F>& p, void* out) {
+  Affine<F> a = p.to_affine();
+  a.x = a.x.from_mont();
+  a.y = a.y.from_mont();
+  a.store(out);
+}
+
+// Proof assembly (K15).  One CTA, four warps; lane 0 of each warp works:
+//  phase 1: w0: r*delta1   w1: s*delta1   w2: s*delta2   w3: (r*s)*delta1
+//  phase 2: w0: A = alpha + msm_a + r*delta1 ; s*A      w1: B1 = beta1 + msm_b1 + s*delta1 ; r*B1
+//           w2: B2 = beta2 + msm_b2 + s*delta2
+//  phase 3: w0: C = msm_l + msm_h + s*A + r*B1 - rs*delta1
+// results: canonical affine; fixed: Montgomery affine; rs: r | s canonical; proof: A | B2 | C.
+__global__ void groth16_assemble_kernel(const uint8_t* results, const uint8_t* fixed,
+                                        const uint32_t* rs, uint8_t* proof) {
+  __shared__ uint4 sm_raw[(4 * sizeof(G1XYZZ) + sizeof(G2XYZZ)) / 16];
+  G1XYZZ* s1 = reinterpret_cast<G1XYZZ*>(sm_raw);            // [0] r*d1 -> s*A, [1] s*d1 -> r*B1, [2] rs*d1
+  G2XYZZ* s2 = reinterpret_cast<G2XYZZ*>(s1 + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t r[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { r[i] = rs[i]; s[i] = rs[8 + i]; }
+  const G1Affine alpha = G1Affine::load(fixed), beta1 = G1Affine::load(fixed + 64),
+                 delta1 = G1Affine::load(fixed + 128);
+  if (lane == 0) {
+    if (warp == 0) mul_scalar(G1XYZZ::from_affine(delta1), r).store(s1 + 0);
+    if (warp == 1) mul_scalar(G1XYZZ::from_affine(delta1), s).store(s1 + 1);
+    if (warp == 2) {
+      G2Affine delta2 = G2Affine::load(fixed + 192 + 128);
+      mul_scalar(G2XYZZ::from_affine(delta2), s).store(s2);
+    }
+    if (warp == 3) {
+      Fr rm, sm;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { rm.v[i] = r[i]; sm.v[i] = s[i]; }
+      Fr prod = (rm.to_mont() * sm.to_mont()).from_mont();
+      mul_scalar(G1XYZZ::from_affine(delta1), prod.v).store(s1 + 2);
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+    if (warp == 0) {
+      G1XYZZ A = G1XYZZ::load(s1 + 0);
+      A.madd(alpha);
+      A.madd(load_canonical_affine<Fq>(results));
+      G1Affine Aa = A.to_affine();
+      G1Affine out = Aa;
+      out.x = out.x.from_mont();
+      out.y = out.y.from_mont();
+      out.store(proof);
+      mul_scalar(G1XYZZ::from_affine(Aa), s).store(s1 + 0);
+    }
+    if (warp == 1) {
+      G1XYZZ B1 = G1XYZZ::load(s1 + 1);
+      B1.madd(beta1);
+      B1.madd(load_canonical_affine<Fq>(results + 64));
+      G1Affine Ba = B1.to_affine();
+      mul_scalar(G1XYZZ::from_affine(Ba), r).store(s1 + 1);
+    }
+    if (warp == 2) {
+      G2XYZZ B2 = G2XYZZ::load(s2);
+      B2.madd(G2Affine::load(fixed + 192));
+      B2.madd(load_canonical_affine<Fq2>(results + 128));
+      store_canonical_affine<Fq2>(B2, proof + 64);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    G1XYZZ Cc = G1XYZZ::load(s1 + 0);
+    Cc.add(G1XYZZ::load(s1 + 1));
+    Cc.add(G1XYZZ::load(s1 + 2).neg());
+    Cc.madd(load_canonical_affine<Fq>(results + 256));
+    Cc.madd(load_canonical_affine<Fq>(results + 320));
+    store_canonical_affine<Fq>(Cc, proof + 192);
+  }
+}
+
+// ---------------------------------------------------------------- host helpers
+static void hfr_words(const HFr& a, uint32_t out[8]) { std::memcpy(out, a.l, 32); }
+
+struct HostR1CS {
+  uint64_t m, ncons;
+  std::vector<uint32_t> row_ptr[3], col[3], cidx[3];
+  std::vector<uint32_t> coeff_values;   // small integer coefficients, index = cidx
+};
+
+// The synthetic chain circuit: constraint j <= m-5: (z[j+2] + (j%7+1)) * z[j+3] = z[j+4];
+// then z[m-1] * z[m-2] = z[1]; then (z[1] + z[2]) * 1 = z[1] + z[2].
+static HostR1CS synthetic_r1cs(uint32_t log_n) {
+  HostR1CS cs;
+  cs.m = 1ull << log_n;
+  const uint64_t m = cs.m;
+  for (uint32_t v = 0; v <= 7; v++) cs.coeff_values.push_back(v);   // cidx == coefficient value
+  auto push = [&](int mat, std::initializer_list<std::pair<uint32_t, uint32_t>> row) {
+    for (auto& e : row) {
+      cs.col[mat].push_back(e.first);
+      cs.cidx[mat].push_back(e.second);
+    }
+    cs.row_ptr[mat].push_back(uint32_t(cs.col[mat].size()));
+  };
+  for (int k = 0; k < 3; k++) cs.row_ptr[k].push_back(0);
+  for (uint64_t j = 0; j + 4 < m; j++) {
+    push(0, {{0u, uint32_t(j % 7 + 1)}, {uint32_t(j + 2), 1u}});
+    push(1, {{uint32_t(j + 3), 1u}});
+    push(2, {{uint32_t(j + 4), 1u}});
+  }
+  push(0, {{uint32_t(m - 1), 1u}});
+  push(1, {{uint32_t(m - 2), 1u}});
+  push(2, {{1u, 1u}});
+  push(0, {{1u, 1u}, {2u, 1u}});
+  push(1, {{0u, 1u}});
+  push(2, {{1u, 1u}, {2u, 1u}});
+  cs.ncons = cs.row_ptr[0].size() - 1;
+  return cs;
+}
+
+static HFr hpow_u64(HFr b, uint64_t e) {
+  HFr r = HFr::one();
+  while (e) {
+    if (e & 1) r = r * b;
+    b = b.sqr();
+    e >>= 1;
+  }
+  return r;
+}
+
+template <class T>
+static cudaError_t upload_vec(const std::vector<T>& v, T** d, cudaStream_t s) {
+  cudaError_t e = cudaMalloc(d, (v.size() ? v.size() : 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+static int make_query(zkb_ctx* ctx, const std::vector<uint64_t>& scalars_canon, uint64_t count,
+                      int is_g2, zkb_bases** out) {
+  zkb_bases* b = new (std::nothrow) zkb_bases();
+  if (!b) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  b->device = ctx->device;
+  b->is_g2 = is_g2;
+  b->n = count;
+  cudaError_t e = cudaMalloc(&b->d_pts, (count ? count : 1) * (is_g2 ? 128 : 64));
+  if (e != cudaSuccess) {
+    delete b;
+    return cuda_fail(ctx, e, "query allocation");
+  }
+  *out = b;
+  ZKB_CUDA(ctx, ctx->io_a.ensure(count * 32 + 32));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars_canon.data(), count * 32,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  int rc = bases_from_scalars(ctx, ctx->io_a.p, count, is_g2, b->d_pts);
+  if (rc) return rc;
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // scalars_canon may die after return
+  return ZKB_OK;
+}
+
+static void canon_into(const HFr& a, std::vector<uint64_t>& v, uint64_t i) {
+  HFr c = a.from_mont();
+  std::memcpy(&v[4 * i], c.l, 32);
+}
+
+}  // namespace zkb
+
+extern "C" {
+
+void zkb_pk_free(zkb_pk* pk) {
+  if (!pk) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(pk->device);
+  zkb_bases_free(pk->a_query);
+  zkb_bases_free(pk->b_g1_query);
+  zkb_bases_free(pk->b_g2_query);
+  zkb_bases_free(pk->l_query);
+  zkb_bases_free(pk->h_query);
+  void* ptrs[] = {pk->d_fixed, pk->d_coeff_table, pk->d_a, pk->d_b, pk->d_c, pk->d_z, pk->d_zm,
+                  pk->d_results, pk->d_proof};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int k = 0; k < 3; k++) {
+    if (pk->d_row_ptr[k]) cudaFree(pk->d_row_ptr[k]);
+    if (pk->d_col[k]) cudaFree(pk->d_col[k]);
+    if (pk->d_cidx[k]) cudaFree(pk->d_cidx[k]);
+  }
+  cudaSetDevice(cur);
+  delete pk;
+}
+
+const zkb_bases* zkb_pk_query(const zkb_pk* pk, int which) {
+  if (!pk) return nullptr;
+  switch (which) {
+    case 0: return pk->a_query;
+    case 1: return pk->b_g1_query;
+    case 2: return pk->b_g2_query;
+    case 3: return pk->l_query;
+    case 4: return pk->h_query;
+    default: return nullptr;
+  }
+}
+
+int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
+                          uint8_t* z_out) {
+  if (log_n < 3 || log_n > 28 || !w0 || !w1 || !z_out) return ZKB_EINVAL;
+  const uint64_t m = 1ull << log_n;
+  HFr a, b;
+  if (!HFr::from_bytes(w0, &a) || !HFr::from_bytes(w1, &b)) return ZKB_EINVAL;
+  std::vector<HFr> z;
+  try {
+    z.assign(m, HFr::zero());
+  } catch (...) {
+    return ZKB_ENOMEM;
+  }
+  HFr small[8];
+  for (int i = 0; i < 8; i++) small[i] = HFr::from_u64(i);
+  z[0] = HFr::one();
+  z[2] = a;
+  z[3] = b;
+  for (uint64_t j = 0; j + 4 < m; j++) z[j + 4] = (z[j + 2] + small[j % 7 + 1]) * z[j + 3];
+  z[1] = z[m - 1] * z[m - 2];
+  for (uint64_t i = 0; i < m; i++) z[i].to_bytes(z_out + 32 * i);
+  return ZKB_OK;
+}
+
+int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
+                     uint8_t vk_out[ZKB_VK_BYTES]) {
+  if (!ctx) return ZKB_EINVAL;
+  BusyGuard guard(ctx);
+  if (!guard.ok) return ZKB_EBUSY;
+  if (!out || !vk_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (log_n < 3 || log_n > 26) return set_error(ctx, ZKB_EINVAL, "log_n must be in [3, 26]");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  zkb_pk* pk = new (std::nothrow) zkb_pk();
+  if (!pk) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  int rc = ZKB_OK;
+  try {
+    HostR1CS cs = synthetic_r1cs(log_n);
+    const uint64_t n = 1ull << log_n, m = cs.m;
+    pk->device = ctx->device;
+    pk->log_n = log_n;
+    pk->n = n;
+    pk->m = m;
+    pk->ncons = cs.ncons;
+    host::Xoshiro256ss rng(seed);
+    HFr tau = rng.fr(), alpha = rng.fr(), beta = rng.fr(), gamma = rng.fr(), delta = rng.fr();
+    // Lagrange basis at tau
+    uint32_t wroot[8];
+    host_fr_root(log_n, 0, wroot);
+    HFr w;
+    std::memcpy(w.l, wroot, 32);
+    HFr zt = hpow_u64(tau, n) - HFr::one();
+    HFr ninv = hpow_u64(HFr::from_u64(2), log_n).inverse();
+    std::vector<HFr> L(n), den(n), pre(n);
+    HFr wj = HFr::one(), scale = zt * ninv;
+    for (uint64_t j = 0; j < n; j++) {
+      den[j] = tau - wj;
+      L[j] = scale * wj;
+      wj = wj * w;
+    }
+    HFr acc = HFr::one();
+    for (uint64_t j = 0; j < n; j++) {
+      pre[j] = acc;
+      acc = acc * den[j];
+    }
+    HFr ia = acc.inverse();
+    for (uint64_t j = n; j-- > 0;) {
+      L[j] = L[j] * (ia * pre[j]);
+      ia = ia * den[j];
+    }
+    std::vector<HFr> u(m, HFr::zero()), v(m, HFr::zero()), wv(m, HFr::zero());
+    std::vector<HFr> coeff_m;
+    for (uint32_t c : cs.coeff_values) coeff_m.push_back(HFr::from_u64(c));
+    std::vector<HFr>* uvw[3] = {&u, &v, &wv};
+    for (int k = 0; k < 3; k++)
+      for (uint64_t j = 0; j < cs.ncons; j++)
+        for (uint32_t e = cs.row_ptr[k][j]; e < cs.row_ptr[k][j + 1]; e++) {
+          HFr& t = (*uvw[k])[cs.col[k][e]];
+          t = t + coeff_m[cs.cidx[k][e]] * L[j];
+        }
+    for (uint64_t i = 0; i < 2; i++) u[i] = u[i] + L[cs.ncons + i];
+    HFr gi = gamma.inverse(), di = delta.inverse();
+    // scalars (canonical) for every query; one reusable staging vector
+    std::vector<uint64_t> sc(4 * n);
+    for (uint64_t i = 0; i < m; i++) canon_into(u[i], sc, i);
+    if ((rc = make_query(ctx, sc, m, 0, &pk->a_query))) throw rc;
+    for (uint64_t i = 0; i < m; i++) canon_into(v[i], sc, i);
+    if ((rc = make_query(ctx, sc, m, 0, &pk->b_g1_query))) throw rc;
+    if ((rc = make_query(ctx, sc, m, 1, &pk->b_g2_query))) throw rc;
+    HFr abc[2];
+    for (uint64_t i = 0; i < m; i++) {
+      HFr t = beta * u[i] + alpha * v[i] + wv[i];
+      if (i < 2) abc[i] = t * gi;
+      else canon_into(t * di, sc, i - 2);
+    }
+    if ((rc = make_query(ctx, sc, m - 2, 0, &pk->l_query))) throw rc;
+    HFr tp = zt * di;
+    for (uint64_t i = 0; i + 1 < n; i++) {
+      canon_into(tp, sc, i);
+      tp = tp * tau;
+    }
+    if ((rc = make_query(ctx, sc, n - 1, 0, &pk->h_query))) throw rc;
+    // fixed points: [alpha, beta, delta, ic0, ic1] * G1 and [beta, delta, gamma] * G2
+    std::vector<uint64_t> f1(4 * 5), f2(4 * 3);
+    canon_into(alpha, f1, 0); canon_into(beta, f1, 1); canon_into(delta, f1, 2);
+    canon_into(abc[0], f1, 3); canon_into(abc[1], f1, 4);
+    canon_into(beta, f2, 0); canon_into(delta, f2, 1); canon_into(gamma, f2, 2);
+    zkb_bases *b1 = nullptr, *b2 = nullptr;
+    if ((rc = make_query(ctx, f1, 5, 0, &b1))) throw rc;
+    if ((rc = make_query(ctx, f2, 3, 1, &b2))) { zkb_bases_free(b1); throw rc; }
+    cudaError_t e = cudaMalloc(&pk->d_fixed, 3 * 64 + 2 * 128);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pk->d_fixed, b1->d_pts, 3 * 64, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((char*)pk->d_fixed + 192, b2->d_pts, 2 * 128, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // vk (canonical bytes): alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | ic0 | ic1
+    uint8_t g1c[5 * 64], g2c[3 * 128];
+    int r1 = bases_download_nolock(ctx, b1, 0, 5, g1c);
+    int r2 = bases_download_nolock(ctx, b2, 0, 3, g2c);
+    zkb_bases_free(b1);
+    zkb_bases_free(b2);
+    if (e != cudaSuccess) throw cuda_fail(ctx, e, "fixed points");
+    if (r1 || r2) throw (r1 ? r1 : r2);
+    std::memcpy(vk_out, g1c, 64);
+    std::memcpy(vk_out + 64, g2c, 128);
+    std::memcpy(vk_out + 192, g2c + 256, 128);
+    std::memcpy(vk_out + 320, g2c + 128, 128);
+    std::memcpy(vk_out + 448, g1c + 192, 128);
+    // matrices
+    for (int k = 0; k < 3; k++) {
+      if ((e = upload_vec(cs.row_ptr[k], &pk->d_row_ptr[k], ctx->stream)) != cudaSuccess ||
+          (e = upload_vec(cs.col[k], &pk->d_col[k], ctx->stream)) != cudaSuccess ||
+          (e = upload_vec(cs.cidx[k], &pk->d_cidx[k], ctx->stream)) != cudaSuccess)
+        throw cuda_fail(ctx, e, "matrix upload");
+    }
+    std::vector<uint32_t> ctab(8 * coeff_m.size());
+    for (size_t i = 0; i < coeff_m.size(); i++) hfr_words(coeff_m[i], &ctab[8 * i]);
+    uint32_t* d_ct = nullptr;
+    if ((e = upload_vec(ctab, &d_ct, ctx->stream)) != cudaSuccess) throw cuda_fail(ctx, e, "coeff upload");
+    pk->d_coeff_table = d_ct;
+    void** work[] = {&pk->d_a, &pk->d_b, &pk->d_c, &pk->d_z, &pk->d_zm};
+    for (void** wp : work)
+      if ((e = cudaMalloc(wp, n * 32)) != cudaSuccess) throw cuda_fail(ctx, e, "work vectors");
+    if ((e = cudaMalloc(&pk->d_results, ZKB_INTERMEDIATE_BYTES)) != cudaSuccess ||
+        (e = cudaMalloc(&pk->d_proof, ZKB_PROOF_BYTES + 64)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+      throw cuda_fail(ctx, e, "result buffers");
+  } catch (int code) {
+    zkb_pk_free(pk);
+    return code;
+  } catch (const std::bad_alloc&) {
+    zkb_pk_free(pk);
+    return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  }
+  *out = pk;
+  return ZKB_OK;
+}
+
+int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
+                      const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
+                      uint8_t* intermediates_opt, uint8_t* h_out_opt,
+                      zkb_prove_timings* timings_opt) {
+  if (!ctx) return ZKB_EINVAL;
+  BusyGuard guard(ctx);
+  if (!guard.ok) return ZKB_EBUSY;
+  if (!pk || !witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (pk->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "proving key lives on another device");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = pk->n, m = pk->m;
+  {
+    uint64_t w[4];
+    std::memcpy(w, r, 32);
+    bool ok = HFr::lt_mod(w);
+    std::memcpy(w, s, 32);
+    ok = ok && HFr::lt_mod(w);
+    for (uint64_t i = 0; ok && i < m; i++) {
+      std::memcpy(w, witness + 32 * i, 32);
+      ok = HFr::lt_mod(w);
+    }
+    if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in witness / r / s");
+  }
+  cudaStream_t st = ctx->stream;
+  enum { E_START, E_H2D, E_SPMV, E_NTT, E_A, E_B1, E_B2, E_L, E_H, E_END, E_COUNT };
+  cudaEvent_t ev[E_COUNT];
+  for (int i = 0; i < E_COUNT; i++) ZKB_CUDA(ctx, cudaEventCreate(&ev[i]));
+  auto mark = [&](int i) { cudaEventRecord(ev[i], st); };
+  int rc = ZKB_OK;
+  do {
+    mark(E_START);
+    cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES, r, 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES + 32, s, 32, cudaMemcpyHostToDevice, st);
+    mark(E_H2D);
+    const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
+    fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
+    void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
+    for (int k = 0; k < 3; k++)
+      r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
+                                             (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
+                                             (Fr*)outs[k], pk->ncons, n, k == 0, 2);
+    mark(E_SPMV);
+    CosetTables* ct;
+    if ((rc = coset_tables(ctx, pk->log_n, &ct))) break;
+    for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 1, nullptr, nullptr, 0, 1, 1);
+    for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 0, ct->fwd.p, nullptr, 0, 1, 1);
+    if (rc) break;
+    qap_pointwise_kernel<<<bl_n, 256, 0, st>>>((Fr*)pk->d_a, (const Fr*)pk->d_b, (const Fr*)pk->d_c, n);
+    // coset iNTT with g^{-i} / Z(g) folded into the output table; result canonical = h
+    if ((rc = ntt_run(ctx, pk->d_a, pk->d_a, pk->log_n, 1, nullptr, ct->inv_z.p, 0, 1, 0))) break;
+    mark(E_NTT);
+    char* res = (char*)pk->d_results;
+    if ((rc = msm_exec(ctx, pk->a_query, 0, pk->d_z, m, res))) break;
+    mark(E_A);
+    if ((rc = msm_exec(ctx, pk->b_g1_query, 0, pk->d_z, m, res + 64))) break;
+    mark(E_B1);
+    if ((rc = msm_exec(ctx, pk->b_g2_query, 0, pk->d_z, m, res + 128))) break;
+    mark(E_B2);
+    if ((rc = msm_exec(ctx, pk->l_query, 0, (char*)pk->d_z + 64, m - 2, res + 256))) break;
+    mark(E_L);
+    if ((rc = msm_exec(ctx, pk->h_query, 0, pk->d_a, n - 1, res + 320))) break;
+    mark(E_H);
+    groth16_assemble_kernel<<<1, 128, 0, st>>>((const uint8_t*)pk->d_results, (const uint8_t*)pk->d_fixed,
+                                               (const uint32_t*)((char*)pk->d_proof + ZKB_PROOF_BYTES),
+                                               (uint8_t*)pk->d_proof);
+    cudaMemcpyAsync(proof_out, pk->d_proof, ZKB_PROOF_BYTES, cudaMemcpyDeviceToHost, st);
+    mark(E_END);
+    if (intermediates_opt)
+      cudaMemcpyAsync(intermediates_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
+    if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      rc = cuda_fail(ctx, e, "groth16 prove");
+      break;
+    }
+    if (timings_opt) {
+      float* f[] = {&timings_opt->ms_h2d, &timings_opt->ms_spmv, &timings_opt->ms_ntt,
+                    &timings_opt->ms_msm_a, &timings_opt->ms_msm_b1, &timings_opt->ms_msm_b2,
+                    &timings_opt->ms_msm_l, &timings_opt->ms_msm_h};
+      for (int i = 0; i < 8; i++) cudaEventElapsedTime(f[i], ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_END]);
+    }
+  } while (0);
+  for (int i = 0; i < E_COUNT; i++) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
+}  // extern "C"

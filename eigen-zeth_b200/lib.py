@@ -20,7 +20,7 @@ EXPORTS = [
     "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
-    "zkb_pk_synthetic", "zkb_pk_free", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_pk_synthetic", "zkb_pk_free", "zkb_pk_query", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe",
 ]
 
@@ -79,6 +79,8 @@ def load_library() -> C.CDLL:
         lib.zkb_pk_synthetic.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
         lib.zkb_pk_free.argtypes = [vp]
         lib.zkb_pk_free.restype = None
+        lib.zkb_pk_query.argtypes = [vp, i32]
+        lib.zkb_pk_query.restype = vp
         lib.zkb_synthetic_witness.argtypes = [u32, u8p, u8p, vp]
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
@@ -120,9 +122,23 @@ class Bases:
             pass
 
 
+class BorrowedBases(Bases):
+    """view of bases owned by a proving key: never freed from here."""
+
+    def free(self):
+        self.handle = None
+
+
 class ProvingKey:
     def __init__(self, ctx, handle, vk: bytes, log_n: int):
         self.ctx, self.handle, self.vk, self.log_n = ctx, handle, vk, log_n
+
+    def query(self, which: int) -> "Bases":
+        """borrowed view of a query (0 a, 1 b_g1, 2 b_g2, 3 l, 4 h)."""
+        h = self.ctx.lib.zkb_pk_query(self.handle, which)
+        if not h:
+            raise ValueError("no such query")
+        return BorrowedBases(self.ctx, C.c_void_p(h), which == 2)
 
     def free(self):
         if self.handle:

@@ -92,6 +92,9 @@ int zkb_g2_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[128]
 int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
                      uint8_t vk_out[ZKB_VK_BYTES]);
 void zkb_pk_free(zkb_pk* pk);
+/* borrowed handle to one query of the key: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 l_query,
+ * 4 h_query (ark-groth16 ProvingKey field names); valid until zkb_pk_free; do not free it */
+const zkb_bases* zkb_pk_query(const zkb_pk* pk, int which);
 /* full witness assignment z (2^log_n canonical Fr, z[0] = 1, z[1] = public input) from two seeds */
 int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
                           uint8_t* z_out);

@@ -1,0 +1,82 @@
+"""Groth16 prove on the GPU vs oracle B (bit-exact with identical r, s) + pairing verification."""
+import pytest
+
+import oracle_a as o
+import oracle_b as ob
+from helpers import fr_bytes, fr_list, g1_list, g2_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed):
+    rng = o.Xoshiro256ss(seed)
+    return [fr_bytes([rng.fr()]) for _ in range(4)]
+
+
+@pytest.mark.parametrize("log_n", [3, 4, 6, 8, 9, 11, 14])
+def test_prove_bit_exact_vs_oracle(ctx, zkb, log_n):
+    seed = 0x5EED0004 + log_n
+    pk = ctx.pk_synthetic(log_n, seed)
+    opk = ob.ProvingKey(log_n, seed)
+    assert pk.vk == opk.vk()
+    for which in range(5):
+        assert pk.query(which).download() == opk.query(which), "query %d" % which
+    w0, w1, r, s = _inputs(seed + 1)
+    wit = zkb.synthetic_witness(log_n, w0, w1)
+    assert wit == ob.synthetic_witness(log_n, w0, w1)
+    proof, inter, h, timings = ctx.groth16_prove(pk, wit, r, s, want_intermediates=True, want_h=True)
+    oproof, ointer, oh, _ = opk.prove(wit, r, s)
+    assert h == oh
+    assert inter == ointer
+    assert proof == oproof
+    assert zkb.groth16_verify(pk.vk, proof, wit[32:64])
+    bad = bytearray(wit[32:64])
+    bad[0] ^= 1
+    assert not zkb.groth16_verify(pk.vk, proof, bytes(bad))
+    # replay with the same (r, s) is bit-identical (idempotent GenFinalProof, provider.rs:245-274)
+    proof2, _, _, _ = ctx.groth16_prove(pk, wit, r, s)
+    assert proof2 == proof
+    # different blinding -> different but still valid proof
+    proof3, _, _, _ = ctx.groth16_prove(pk, wit, s, r)
+    assert proof3 != proof and zkb.groth16_verify(pk.vk, proof3, wit[32:64])
+    pk.free()
+    opk.free()
+
+
+def test_prove_small_vs_oracle_a(ctx, zkb):
+    """one size also against the pure-Python oracle, including its independent pairing."""
+    log_n, seed = 4, 99
+    pk = ctx.pk_synthetic(log_n, seed)
+    rng = o.Xoshiro256ss(seed)
+    tw = [rng.fr() for _ in range(5)]
+    cs = o.synthetic_r1cs(log_n)
+    pka, vka = o.groth16_setup(cs, *tw)
+    assert g1_list(pk.query(0).download()) == pka["a_query"]
+    assert g2_list(pk.query(2).download()) == pka["b_g2_query"]
+    w0, w1, r, s = _inputs(7)
+    wit = zkb.synthetic_witness(log_n, w0, w1)
+    z = fr_list(wit)
+    assert z == o.synthetic_witness(log_n, fr_list(w0)[0], fr_list(w1)[0])
+    proof, _, _, _ = ctx.groth16_prove(pk, wit, r, s)
+    pa, _ = o.groth16_prove(pka, cs, z, fr_list(r)[0], fr_list(s)[0])
+    got = (o.g1_from_bytes(proof[:64]), o.g2_from_bytes(proof[64:192]), o.g1_from_bytes(proof[192:]))
+    assert got == pa
+    assert o.groth16_verify(vka, got, [z[1]])
+
+
+@pytest.mark.parametrize("log_n", [18, 20])
+def test_prove_large_pairing_verified(ctx, zkb, log_n):
+    seed = 0x5EED0004 + log_n
+    pk = ctx.pk_synthetic(log_n, seed)
+    w0, w1, r, s = _inputs(seed)
+    wit = zkb.synthetic_witness(log_n, w0, w1)
+    proof, _, _, t = ctx.groth16_prove(pk, wit, r, s)
+    assert zkb.groth16_verify(pk.vk, proof, wit[32:64])
+    assert not zkb.groth16_verify(pk.vk, proof, wit[64:96])
+    # a corrupted witness entry must not verify
+    badw = bytearray(wit)
+    badw[32 * 1000] ^= 1
+    proof_bad, _, _, _ = ctx.groth16_prove(pk, bytes(badw), r, s)
+    assert not zkb.groth16_verify(pk.vk, proof_bad, wit[32:64])
+    print("prove 2^%d: %s" % (log_n, t))
+    pk.free()
