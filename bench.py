@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on B200: G1 MSM Mpts/s at 2^24 (primary), with the Fr NTT
+Gelem/s at 2^24 and the Groth16 prove latency at 2^22 constraints as extra keys.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one 2^24-point G1 MSM per GPU (point-range sharding: rank g owns points
+[g*2^24, (g+1)*2^24) of an N*2^24-point MSM; the only exchange is an all-gather of one 64-byte
+partial result per rank followed by N-1 point additions) — weak scaling.
+  value : device-timed, scalars already resident in HBM (512 MiB per rank, larger than the 126 MB L2)
+  e2e   : the same MSM through the C ABI with HOST scalars (pinned): H2D copy + MSM + D2H of the result
+--impl reference times the CPU oracle (arkworks-style Pippenger, all host threads) on a bounded
+sample of the same workload; it never touches the GPU library.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+LOG_N = 24
+SEED = 0x5EED0000
+CPU_SAMPLE_LOG = 20
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """NVML SM clock + throttle reasons, sampled every 100 ms during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline_msm(sample_log=CPU_SAMPLE_LOG, reps=1):
+    """oracle B (arkworks-style VariableBaseMSM restatement) on all host threads; bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_b as ob
+    n = 1 << sample_log
+    bases = ob.synthetic_bases(n, SEED + 1)
+    scalars = ob.random_scalars(n, SEED + sample_log)
+    best, out = None, None
+    for _ in range(reps):
+        out, t = ob.msm_g1(bases, scalars)
+        best = t if best is None else min(best, t)
+    return {"value": n / best / 1e6, "unit": "Mpts/s", "cores": ob.threads(), "kind": "port",
+            "sample": "2^%d-point G1 MSM, uniform scalars, same generator as the GPU run (%.2f s)" % (sample_log, best)}, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_b as ob
+    n = 1 << CPU_SAMPLE_LOG
+    bases = ob.synthetic_bases(n, SEED + 1)
+    scalars = ob.random_scalars(n, SEED + CPU_SAMPLE_LOG)
+    for _ in range(args.warmup):
+        ob.msm_g1(bases, scalars)
+    t0 = time.perf_counter()
+    inner = 0.0
+    for _ in range(args.steps):
+        _, t = ob.msm_g1(bases, scalars)
+        inner += t
+    wall = time.perf_counter() - t0
+    value = n * args.steps / inner / 1e6
+    sample = "each step: one 2^%d-point G1 MSM (bounded sample of the 2^%d workload), %d host threads" % (
+        CPU_SAMPLE_LOG, LOG_N, ob.threads())
+    print(json.dumps({
+        "impl": "reference", "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * inner / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)",
+        "data": "synthetic",
+        "config": {"workload": "G1 MSM, 2^%d points per GPU (BASELINE.json configs[1])" % LOG_N, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": ob.threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zkb")
+    ap.add_argument("--log-n", type=int, default=LOG_N)
+    ap.add_argument("--no-extras", action="store_true", help="skip the NTT / Groth16 / CPU legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import eigen_zeth_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = z.Context(local)          # raises without an sm_100 GPU — no CPU fallback
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    log_n = args.log_n
+    n = 1 << log_n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: this rank's shard of the bases and scalars
+    bases = ctx.synthetic_bases(n, SEED + 1 + 1000 * rank)
+    g = torch.Generator(device="cpu").manual_seed(SEED + log_n + 7919 * rank)
+    sc_host = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, generator=g)
+    sc_host[:, 7] &= 0x0FFFFFFF                     # < 2^252 < r: canonical scalars
+    sc_host = sc_host.pin_memory()
+    sc_dev = sc_host.to(dev, non_blocking=False)
+    part = torch.zeros(64, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * 64, dtype=torch.uint8, device=dev)
+    total = torch.zeros(64, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        ctx.msm_dev(bases, sc_dev.data_ptr(), n, part.data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, part)
+            ctx.point_sum_dev(gathered.data_ptr(), world, total.data_ptr())
+
+    def step_e2e():
+        res = ctx.msm_raw(bases, sc_host.data_ptr(), n)       # H2D + MSM + D2H inside the C ABI
+        if world > 1:
+            part.copy_(torch.frombuffer(bytearray(res), dtype=torch.uint8))
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, part)
+            ctx.point_sum_dev(gathered.data_ptr(), world, total.data_ptr())
+            ctx.sync()
+            res = bytes(total.cpu().numpy())
+        return res
+
+    # ---- value: device-resident
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * n * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- e2e: host scalars through the C ABI
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(te.item()) / 1e6
+
+    # ---- roofline of the dominant kernel (level-1 bucket accumulation), timed live with CUDA events
+    ctx.set("msm_profile", 1)
+    stage = {}
+    for _ in range(3):
+        ctx.msm_dev(bases, sc_dev.data_ptr(), n, part.data_ptr())
+        t = ctx.msm_last_timings()
+        for k, v in t.items():
+            stage.setdefault(k, []).append(v)
+    ctx.set("msm_profile", 0)
+    stage = {k: statistics.median(v) for k, v in stage.items()}
+    pipe = ctx.bench_int_pipe(3000)
+    c = 16 if log_n >= 22 else max(4, log_n - 6)
+    nwin = (255 + c - 1) // c
+    imads = n * nwin * 10 * 136                       # madds * 10 modmul * 136 wide IMAD
+    achieved = imads / (stage["accumulate_l1"] * 1e-3)
+    hbm_peak, hbm_src = _peaks()
+    roofline = {
+        "bound": "int_pipe", "kernel": "msm_accumulate_l1_kernel<Fq>", "achieved": achieved / 1e12,
+        "peak": pipe["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE.U32/s",
+        "frac": achieved / pipe["imad_wide_per_s"], "traffic": None,
+        "peak_source": "measured live by zkb_bench_int_pipe (IMAD.WIDE.U32 carry chains); MEASURED_PEAKS.json has no integer-pipe peak",
+        "algorithmic_ops_per_launch": imads, "window_bits": c, "windows": nwin,
+        "kernel_ms": stage["accumulate_l1"], "stage_ms": stage,
+        "whole_msm_frac": imads / (ms_total / args.steps * 1e-3) / pipe["imad_wide_per_s"],
+        "hbm_view": {"algorithmic_bytes": n * nwin * (64 + 8), "achieved_GBps": n * nwin * 72 / (stage["accumulate_l1"] * 1e-3) / 1e9,
+                     "peak_GBps": hbm_peak, "peak_source": hbm_src},
+    }
+
+    line = {
+        "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "G1 MSM, 2^%d points per GPU (BASELINE.json configs[1])" % log_n,
+                   "global_points": world * n, "sharding": "point range per rank + all-gather of one 64 B partial",
+                   "window_bits": c, "l2": "inputs (512 MiB scalars + 1 GiB bases per rank) larger than the 126 MB L2",
+                   "timing": "CUDA events on the library stream, max over ranks"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 64},
+        "roofline": roofline, "wall_s": wall,
+    }
+
+    if rank == 0 and not args.no_extras and world == 1:
+        # ---- NTT 2^24 (device resident, Montgomery in/out) and Groth16 2^22
+        x = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev)
+        x[:, 7] &= 0x0FFFFFFF
+        ntt = {}
+        for full in (0, 1):
+            ctx.set("ntt_full_twiddles", full)
+            for _ in range(3):
+                ctx.fr_ntt_dev(x.data_ptr(), x.data_ptr(), log_n, montgomery=True)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(args.steps):
+                ctx.fr_ntt_dev(x.data_ptr(), x.data_ptr(), log_n, montgomery=True)
+            a1.record(stream)
+            a1.synchronize()
+            t_ms = a0.elapsed_time(a1) / args.steps
+            ntt["full_twiddles" if full else "two_level_twiddles"] = {
+                "ms": t_ms, "gelem_s": n / (t_ms * 1e-3) / 1e9,
+                "frac_int_pipe": 136 * (n // 2) * log_n / (t_ms * 1e-3) / pipe["imad_wide_per_s"],
+                "frac_hbm": 128 * n / (t_ms * 1e-3) / 1e9 / hbm_peak}
+        ctx.set("ntt_full_twiddles", 0)
+        line["ntt_2^%d" % log_n] = ntt
+        del x
+        try:
+            glog = 22
+            pk = ctx.pk_synthetic(glog, SEED + 4)
+            w = z.synthetic_witness(glog, (5).to_bytes(32, "little"), (7).to_bytes(32, "little"))
+            wt = torch.frombuffer(bytearray(w), dtype=torch.uint8).pin_memory()
+            r, s = (11).to_bytes(32, "little"), (13).to_bytes(32, "little")
+            best, proof = None, None
+            for i in range(4):
+                t0 = time.perf_counter()
+                proof, _, _, tm = ctx.groth16_prove(pk, wt.data_ptr(), r, s)
+                dt = time.perf_counter() - t0
+                if i and (best is None or dt < best[0]):
+                    best = (dt, tm)
+            ok = z.groth16_verify(pk.vk, proof, w[32:64])
+            line["groth16_2^22"] = {"prove_ms_e2e": best[0] * 1e3, "device_stage_ms": best[1], "pairing_verified": bool(ok)}
+            pk.free()
+        except Exception as ex:  # never lose the primary line
+            line["groth16_2^22"] = {"error": str(ex)}
+        cpu, cpu_out = cpu_baseline_msm()
+        line["cpu_baseline"] = cpu
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -226,6 +226,7 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     uint32_t CT = 8u << (8 - k);
     uint32_t tiles = uint32_t(n / M) * ((a.S + CT - 1) / CT);
     ntt_launch_pass(a, false, tiles, ctx->stream);
+    ctx->launches++;
     M >>= k;
     log_m -= k;
   }
@@ -247,6 +248,7 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     uint32_t k0_range = 1u << a.first_digit_bits;
     uint32_t tiles = ((k0_range + CT - 1) / CT) << (a.row_bits - a.first_digit_bits);
     ntt_launch_pass(a, true, tiles, ctx->stream);
+    ctx->launches++;
   }
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
@@ -285,6 +287,7 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b) {
   b->window_sums = s.window_sums.p;
   b->result_xyzz = s.result_xyzz.p;
   b->result_affine = s.result_affine.p;
+  b->ev = nullptr;
   return ZKB_OK;
 }
 
@@ -303,6 +306,14 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
   int rc = ensure_msm_buffers(ctx, p, &buf);
   if (rc) return rc;
   buf.result_affine = d_out_affine;
+  ctx->msm_ev_valid = false;
+  if (ctx->msm_profile) {
+    for (int i = 0; i < 6; i++)
+      if (!ctx->msm_ev[i]) ZKB_CUDA(ctx, cudaEventCreate(&ctx->msm_ev[i]));
+    buf.ev = ctx->msm_ev;
+    ctx->msm_ev_valid = true;
+  }
+  ctx->launches += 8;   // digits, count_valid, L1, L2, finish, bucket_reduce, window_sum, horner
   const char* base_ptr = reinterpret_cast<const char*>(b->d_pts) + first * aff;
   if (b->is_g2) msm_run_g2(p, buf, d_scalars, n, base_ptr, ctx->stream);
   else msm_run_g1(p, buf, d_scalars, n, base_ptr, ctx->stream);
@@ -536,6 +547,8 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
                    &s.buckets, &s.part1_keys, &s.part1_pts, &s.part2_keys, &s.part2_pts,
                    &s.group_sums, &s.window_sums, &s.result_xyzz, &s.result_affine};
   for (DevBuf* b : all) b->release();
+  for (int i = 0; i < 6; i++)
+    if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -554,6 +567,10 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
   if (!std::strcmp(key, "msm_window")) {
     if (value < 0 || value > 20 || value == 1) return set_error(ctx, ZKB_EINVAL, "msm_window must be 0 or 2..20");
     ctx->msm_window = value;
+    return ZKB_OK;
+  }
+  if (!std::strcmp(key, "msm_profile")) {
+    ctx->msm_profile = value ? 1 : 0;
     return ZKB_OK;
   }
   if (!std::strcmp(key, "ntt_full_twiddles")) {
@@ -774,6 +791,33 @@ int zkb_g1_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[64])
 }
 int zkb_g2_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[128]) {
   return point_sum(ctx, points, n, out, 1);
+}
+
+static int point_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out, int is_g2) {
+  ZKB_ENTER(ctx);
+  if (!d_out || (!d_points && n)) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (is_g2) msm_sum_affine_g2(d_points, n, d_out, ctx->stream);
+  else msm_sum_affine_g1(d_points, n, d_out, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+int zkb_g1_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out) {
+  return point_sum_dev(ctx, d_points, n, d_out, 0);
+}
+int zkb_g2_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out) {
+  return point_sum_dev(ctx, d_points, n, d_out, 1);
+}
+
+uint64_t zkb_ctx_launches(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zkb_msm_last_timings(zkb_ctx* ctx, float ms_out[5]) {
+  ZKB_ENTER(ctx);
+  if (!ms_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (!ctx->msm_ev_valid) return set_error(ctx, ZKB_EINVAL, "no profiled MSM (set msm_profile = 1 first)");
+  ZKB_CUDA(ctx, cudaEventSynchronize(ctx->msm_ev[5]));
+  for (int i = 0; i < 5; i++) ZKB_CUDA(ctx, cudaEventElapsedTime(&ms_out[i], ctx->msm_ev[i], ctx->msm_ev[i + 1]));
+  return ZKB_OK;
 }
 
 // ---- test hooks

@@ -74,6 +74,10 @@ struct zkb_ctx {
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   int64_t msm_window = 0;
   int64_t ntt_full_twiddles = 0;
+  int64_t msm_profile = 0;
+  cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool msm_ev_valid = false;
+  uint64_t launches = 0;                   // kernels of this library launched so far
 
   zkb::DevBuf stage_fwd, stage_inv;        // 255-entry stage twiddle tables
   std::map<uint64_t, zkb::NttDomain*> domains;   // key = log_n * 2 + inverse

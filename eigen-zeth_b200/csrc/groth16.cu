@@ -501,6 +501,7 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     groth16_assemble_kernel<<<1, 128, 0, st>>>((const uint8_t*)pk->d_results, (const uint8_t*)pk->d_fixed,
                                                (const uint32_t*)((char*)pk->d_proof + ZKB_PROOF_BYTES),
                                                (uint8_t*)pk->d_proof);
+    ctx->launches += 6;   // to_mont copy, 3 x SpMV, pointwise, assemble (NTT/MSM count themselves)
     cudaMemcpyAsync(proof_out, pk->d_proof, ZKB_PROOF_BYTES, cudaMemcpyDeviceToHost, st);
     mark(E_END);
     if (intermediates_opt)

@@ -37,6 +37,7 @@ struct MsmBuffers {
   void* window_sums;        // nwin XYZZ
   void* result_xyzz;        // 1 XYZZ (Montgomery)
   void* result_affine;      // 1 affine, canonical little-endian
+  cudaEvent_t* ev;          // optional 6 profiling events: start, digits, sort, L1, L2+finish, tail
 };
 
 MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count);

@@ -94,15 +94,18 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count) {
 
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                          cudaStream_t s) {
+  if (b.ev) cudaEventRecord(b.ev[0], s);
   uint32_t blocks = uint32_t((n + 255) / 256);
   if (blocks)
     msm_digits_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, p.c,
                                              p.nwin, b.keys_in, b.vals_in, 0);
+  if (b.ev) cudaEventRecord(b.ev[1], s);
   size_t temp = p.sort_temp_bytes;
   cub::DeviceRadixSort::SortPairs(b.sort_temp, temp, (const uint32_t*)b.keys_in, b.keys_out,
                                   (const uint32_t*)b.vals_in, b.vals_out, (int64_t)p.m, 0,
                                   p.key_bits, s);
   msm_count_valid_kernel<<<1, 1, 0, s>>>(b.keys_out, p.m, uint32_t(p.n_buckets), b.m_valid);
+  if (b.ev) cudaEventRecord(b.ev[2], s);
 }
 
 }  // namespace zkb

@@ -255,6 +255,7 @@ void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uin
       b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
       reinterpret_cast<P*>(b.buckets), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
       p.l1_threads);
+  if (b.ev) cudaEventRecord(b.ev[3], s);
   msm_accumulate_l2_kernel<F><<<(p.l2_threads + 127) / 128, 128, 0, s>>>(
       b.part1_keys, reinterpret_cast<const P*>(b.part1_pts), 2 * p.l1_threads, p.l2_len,
       reinterpret_cast<P*>(b.buckets), b.part2_keys, reinterpret_cast<P*>(b.part2_pts),
@@ -262,6 +263,7 @@ void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uin
   msm_finish_kernel<F><<<(2 * p.l2_threads + 127) / 128, 128, 0, s>>>(
       b.part2_keys, reinterpret_cast<const P*>(b.part2_pts), 2 * p.l2_threads,
       reinterpret_cast<P*>(b.buckets));
+  if (b.ev) cudaEventRecord(b.ev[4], s);
   msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
       reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
       reinterpret_cast<P*>(b.group_sums));
@@ -271,6 +273,7 @@ void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uin
   msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.nwin, p.c,
                                         reinterpret_cast<P*>(b.result_xyzz),
                                         reinterpret_cast<Affine<F>*>(b.result_affine));
+  if (b.ev) cudaEventRecord(b.ev[5], s);
 }
 
 

@@ -21,7 +21,8 @@ EXPORTS = [
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_free", "zkb_pk_query", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
-    "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe",
+    "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
+    "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
 
 
@@ -87,6 +88,11 @@ def load_library() -> C.CDLL:
     lib.zkb_field_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_curve_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_bench_int_pipe.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    lib.zkb_g1_sum_dev.argtypes = [vp, vp, u32, vp]
+    lib.zkb_g2_sum_dev.argtypes = [vp, vp, u32, vp]
+    lib.zkb_ctx_launches.argtypes = [vp]
+    lib.zkb_ctx_launches.restype = u64
+    lib.zkb_msm_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -243,6 +249,19 @@ class Context:
         fn = self.lib.zkb_g2_sum if g2 else self.lib.zkb_g1_sum
         self._check(fn(self.h, bytes(points), len(points) // sz, out))
         return out.raw
+
+    def point_sum_dev(self, d_points: int, n: int, d_out: int, g2=False):
+        fn = self.lib.zkb_g2_sum_dev if g2 else self.lib.zkb_g1_sum_dev
+        self._check(fn(self.h, d_points, n, d_out))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.zkb_ctx_launches(self.h))
+
+    def msm_last_timings(self):
+        out = (C.c_float * 5)()
+        self._check(self.lib.zkb_msm_last_timings(self.h, out))
+        return dict(zip(("digits", "sort", "accumulate_l1", "accumulate_l2_finish", "reduce_tail"), [float(x) for x in out]))
 
     # ---- Groth16
     def pk_synthetic(self, log_n: int, seed: int) -> ProvingKey:

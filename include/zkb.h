@@ -46,7 +46,7 @@ void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(const zkb_ctx* ctx);
 void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
-/* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1) */
+/* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
 
@@ -82,6 +82,9 @@ int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void*
 /* sum of n affine points (the per-rank partial results of a point-range-sharded MSM) */
 int zkb_g1_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[64]);
 int zkb_g2_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[128]);
+/* the same on device buffers (e.g. the output of an NCCL all-gather), asynchronous */
+int zkb_g1_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out);
+int zkb_g2_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out);
 
 /* ---- Groth16  (GenFinalProofRequest -> FinalProof; prover.proto:130-148) --------------------- */
 /* verifying key layout: alpha_g1 64 | beta_g2 128 | gamma_g2 128 | delta_g2 128 | ic0 64 | ic1 64 */
@@ -127,6 +130,12 @@ int zkb_curve_batch_op(zkb_ctx* ctx, int group, int op, const uint8_t* a, const 
  * results[1] = Montgomery multiplications/s (register resident), results[2] = SM clock (MHz)
  * measured over the run with clock64 */
 int zkb_bench_int_pipe(zkb_ctx* ctx, int iters, double results[3]);
+/* kernels of this library launched through ctx so far (library kernels such as the CUB sort
+ * are not counted) */
+uint64_t zkb_ctx_launches(const zkb_ctx* ctx);
+/* per-stage device times (ms) of the last MSM run with "msm_profile" = 1:
+ * digits | sort | accumulate L1 | accumulate L2 + finish | bucket reduce + window sum + Horner */
+int zkb_msm_last_timings(zkb_ctx* ctx, float ms_out[5]);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus
