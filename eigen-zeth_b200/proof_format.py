@@ -1,0 +1,120 @@
+"""proof.json / public_input.json writer and reader — the output layout eigen-zeth consumes.
+
+Normative layout: reference proof/proof.json:1-22 and proof/public_input.json:1-3 (read at
+src/settlement/worker.rs:56-59).  The reader restates `parse_proof` / `parse_public_input`
+(src/settlement/ethereum/mod.rs:445-481): coordinates are decimal *strings*, pi_b is copied
+unswapped ([c0, c1]), `protocol` / `curve` are ignored, only element 0 of the input array is read,
+and any missing key or non-string value is the error "invalid json data".
+`ProofResult` mirrors src/db/mod.rs:63-71 (serde_json of [u8; 32] is an array of 32 numbers).
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+ERR = "invalid json data"
+
+
+def _le(b: bytes) -> int:
+    return int.from_bytes(b, "little")
+
+
+def proof_to_json(proof: bytes) -> str:
+    """256-byte proof (A 64 | B 128 | C 64, include/zkb.h) -> proof.json text."""
+    if len(proof) != 256:
+        raise ValueError("proof must be 256 bytes")
+    c = [_le(proof[i:i + 32]) for i in range(0, 256, 32)]
+    if any(v >= Q for v in c):
+        raise ValueError("coordinate not reduced modulo q")
+    doc = {
+        "pi_a": {"x": str(c[0]), "y": str(c[1])},
+        "pi_b": {"x": [str(c[2]), str(c[3])], "y": [str(c[4]), str(c[5])]},
+        "pi_c": {"x": str(c[6]), "y": str(c[7])},
+        "protocol": "groth16",
+        "curve": "BN128",
+    }
+    return json.dumps(doc, indent=4)
+
+
+def public_input_to_json(x: bytes) -> str:
+    """32-byte canonical Fr -> public_input.json text (array of exactly one decimal string)."""
+    v = _le(x)
+    if len(x) != 32 or v >= R:
+        raise ValueError("public input must be a canonical 32-byte Fr element")
+    return json.dumps([str(v)], indent=4)
+
+
+def _u256_from_dec_str(v) -> int:
+    # U256::from_dec_str: ASCII digits only, value < 2^256; `.as_str()` fails on non-strings
+    if not isinstance(v, str):
+        raise ValueError(ERR)
+    if not v or not v.isascii() or not v.isdigit():
+        raise ValueError("invalid character in decimal string")
+    n = int(v, 10)
+    if n >> 256:
+        raise ValueError("decimal string overflows U256")
+    return n
+
+
+def _get(v, *path):
+    for p in path:
+        try:
+            v = v[p]
+        except (KeyError, IndexError, TypeError):
+            raise ValueError(ERR)
+    return v
+
+
+def parse_proof(json_str: str):
+    """-> ((ax, ay), ((bx0, bx1), (by0, by1)), (cx, cy)) exactly as the Solidity Proof struct gets them."""
+    v = json.loads(json_str)
+    a = (_u256_from_dec_str(_get(v, "pi_a", "x")), _u256_from_dec_str(_get(v, "pi_a", "y")))
+    b = ((_u256_from_dec_str(_get(v, "pi_b", "x", 0)), _u256_from_dec_str(_get(v, "pi_b", "x", 1))),
+         (_u256_from_dec_str(_get(v, "pi_b", "y", 0)), _u256_from_dec_str(_get(v, "pi_b", "y", 1))))
+    c = (_u256_from_dec_str(_get(v, "pi_c", "x")), _u256_from_dec_str(_get(v, "pi_c", "y")))
+    return a, b, c
+
+
+def parse_public_input(json_str: str):
+    v = json.loads(json_str)
+    return [_u256_from_dec_str(_get(v, 0))]
+
+
+def proof_from_json(json_str: str) -> bytes:
+    a, b, c = parse_proof(json_str)
+    vals = [a[0], a[1], b[0][0], b[0][1], b[1][0], b[1][1], c[0], c[1]]
+    if any(x >= Q for x in vals):
+        raise ValueError("coordinate not reduced modulo q")
+    return b"".join(x.to_bytes(32, "little") for x in vals)
+
+
+def public_input_from_json(json_str: str) -> bytes:
+    (x,) = parse_public_input(json_str)
+    if x >= R:
+        raise ValueError("public input not reduced modulo r")   # NewStateRootNotInsidePrime on-chain
+    return x.to_bytes(32, "little")
+
+
+@dataclass
+class ProofResult:
+    """src/db/mod.rs:63-71; stored under BATCH_PROOF_{n} (src/settlement/worker.rs:179-182)."""
+    block_number: int = 0
+    proof: str = ""
+    public_input: str = ""
+    pre_state_root: bytes = field(default_factory=lambda: bytes(32))
+    post_state_root: bytes = field(default_factory=lambda: bytes(32))
+
+    def to_json(self) -> str:
+        if len(self.pre_state_root) != 32 or len(self.post_state_root) != 32:
+            raise ValueError("state roots must be 32 bytes")       # provider.rs:323-324
+        return json.dumps({"block_number": self.block_number, "proof": self.proof,
+                           "public_input": self.public_input, "pre_state_root": list(self.pre_state_root),
+                           "post_state_root": list(self.post_state_root)})
+
+    @staticmethod
+    def from_json(s: str) -> "ProofResult":
+        d = json.loads(s)
+        return ProofResult(int(d["block_number"]), d["proof"], d["public_input"], bytes(d["pre_state_root"]),
+                           bytes(d["post_state_root"]))
