@@ -1,0 +1,45 @@
+"""Multi-GPU composition of the proving path: one process per GPU, torch.distributed for plumbing.
+
+The MSM is a sum, so rank g owns the point range [g*N/G, (g+1)*N/G); every rank
+reduces its range to ONE affine point with the full single-GPU pipeline and the only exchange is
+an all-gather of 64 B (G1) / 128 B (G2) per rank followed by G-1 point additions.  No data-path
+collective is needed, which is why bench.py reports weak scaling.
+The point arithmetic itself always runs in libzkb.so on the GPU; `combine` below takes the callable
+that sums points so that the host-side logic (ranges, gather, ordering) can be exercised with gloo
+on a machine without GPUs (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """[first, first+count) of rank `rank`; ranges tile [0, n) and differ by at most one point."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, rem = divmod(n, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def all_shards(n: int, world: int) -> List[Tuple[int, int]]:
+    return [shard_range(n, world, r) for r in range(world)]
+
+
+def gather_partials(partial, world: int):
+    """all-gather one fixed-size uint8 tensor per rank -> tensor of shape [world, len]."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return partial.reshape(1, -1)
+    out = torch.empty((world, partial.numel()), dtype=torch.uint8, device=partial.device)
+    dist.all_gather_into_tensor(out.reshape(-1), partial.reshape(-1))
+    return out
+
+
+def sharded_msm(local_msm: Callable[[int, int], "object"], point_sum: Callable[["object"], "object"], n: int,
+                world: int, rank: int):
+    """local_msm(first, count) -> uint8 tensor (affine partial); point_sum(tensor[world, sz]) -> result."""
+    first, count = shard_range(n, world, rank)
+    partial = local_msm(first, count)
+    return point_sum(gather_partials(partial, world))

@@ -1,0 +1,133 @@
+"""CPU-only checks of the product: the C-ABI library loads and exports every symbol include/zkb.h
+declares; host-side logic (witness generation, pairing verifier, proof.json writer/reader, error
+behaviour) matches the oracles; no compute entry point works without a GPU (no CPU fallback)."""
+import json
+import os
+import re
+
+import pytest
+
+import oracle_a as o
+import oracle_b as ob
+from helpers import fr_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "zkb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(zkb):
+    lib = zkb.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(zkb.lib.EXPORTS) == declared
+    assert "sm_100a" in zkb.version()
+
+
+def test_library_is_sm100a_only():
+    """the shipped cubin targets sm_100a and nothing else (no multi-arch fallback)."""
+    import subprocess
+    so = os.path.join(ROOT, "eigen-zeth_b200", "libzkb.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(zkb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.Context(0)
+    assert e.value.code == zkb.lib.ZKB_ENOGPU
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "eigen-zeth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle_a" not in text and "oracle_b" not in text and "oracle/" not in text, f
+
+
+def test_host_witness_matches_oracles(zkb):
+    rng = o.Xoshiro256ss(4)
+    for log_n in (3, 6, 10):
+        w0, w1 = fr_bytes([rng.fr()]), fr_bytes([rng.fr()])
+        got = zkb.synthetic_witness(log_n, w0, w1)
+        assert got == ob.synthetic_witness(log_n, w0, w1)
+        z = [int.from_bytes(got[i:i + 32], "little") for i in range(0, len(got), 32)]
+        assert o.r1cs_is_satisfied(o.synthetic_r1cs(log_n), z) if log_n <= 6 else True
+    with pytest.raises(zkb.ZkbError):
+        zkb.synthetic_witness(4, int(o.R).to_bytes(32, "little"), bytes(32))
+
+
+def test_host_pairing_verifier_against_oracle_proofs(zkb):
+    log_n = 4
+    pk = ob.ProvingKey(log_n, 4242)
+    rng = o.Xoshiro256ss(5)
+    w0, w1, r, s = (fr_bytes([rng.fr()]) for _ in range(4))
+    wit = ob.synthetic_witness(log_n, w0, w1)
+    proof, _, _, _ = pk.prove(wit, r, s)
+    vk = pk.vk()
+    assert zkb.groth16_verify(vk, proof, wit[32:64])
+    bad = bytearray(wit[32:64])
+    bad[0] ^= 1
+    assert not zkb.groth16_verify(vk, proof, bytes(bad))
+    # a well-formed proof of another circuit (the reference fixture) is rejected, not malformed
+    A, B, C = o.parse_proof(GOLDEN["proof_json"])
+    other = o.g1_to_bytes(A) + o.g2_to_bytes(B) + o.g1_to_bytes(C)
+    assert not zkb.groth16_verify(vk, other, wit[32:64])
+    # malformed: off-curve point, non-canonical coordinate, public input >= r
+    off = bytearray(proof)
+    off[0] ^= 1
+    with pytest.raises(zkb.ZkbError):
+        zkb.groth16_verify(vk, bytes(off), wit[32:64])
+    with pytest.raises(zkb.ZkbError):
+        zkb.groth16_verify(vk, int(o.Q).to_bytes(32, "little") + proof[32:], wit[32:64])
+    with pytest.raises(zkb.ZkbError):
+        zkb.groth16_verify(vk, proof, int(o.R).to_bytes(32, "little"))
+    # swapping c0/c1 of B leaves the twist
+    sw = proof[:64] + proof[96:128] + proof[64:96] + proof[160:192] + proof[128:160] + proof[192:]
+    with pytest.raises(zkb.ZkbError):
+        zkb.groth16_verify(vk, sw, wit[32:64])
+
+
+def test_proof_format_matches_reference_layout():
+    from eigen_zeth_b200 import proof_format as pf
+    # reader == the reference's test_parse_proof known answers
+    a, b, c = pf.parse_proof(GOLDEN["test_parse_proof_json"])
+    got = [a[0], a[1], b[0][0], b[0][1], b[1][0], b[1][1], c[0], c[1]]
+    assert got == [int(v) for v in GOLDEN["test_parse_proof_expected"]]
+    assert pf.parse_public_input(GOLDEN["test_parse_public_input_json"]) == [int(GOLDEN["test_parse_public_input_expected"][0])]
+    # writer reproduces the reference's proof/proof.json byte for byte from the parsed coordinates
+    raw = pf.proof_from_json(GOLDEN["proof_json"])
+    assert pf.proof_to_json(raw) == GOLDEN["proof_json"].rstrip("\n")
+    assert json.loads(pf.proof_to_json(raw)) == json.loads(GOLDEN["proof_json"])
+    pub = pf.public_input_from_json(GOLDEN["public_input_json"])
+    assert pf.public_input_to_json(pub) == GOLDEN["public_input_json"].rstrip("\n")
+    # compact form (worker.rs:760-761) parses too; whitespace is free-form
+    assert pf.parse_proof(GOLDEN["worker_compact_proof_json"]) == o.parse_proof(GOLDEN["worker_compact_proof_json"])
+    # error behaviour of parse_proof: missing key / non-string -> "invalid json data"
+    for broken in ('{"pi_a":{"x":"1"}}', '{"pi_a":{"x":1,"y":"2"}}', '[]'):
+        with pytest.raises(ValueError):
+            pf.parse_proof(broken)
+    with pytest.raises(ValueError):
+        pf.parse_public_input("[]")
+    with pytest.raises(ValueError):
+        pf.parse_public_input('["12x"]')
+    with pytest.raises(ValueError):
+        pf.proof_to_json(int(o.Q).to_bytes(32, "little") + bytes(224))
+    pr = pf.ProofResult(7, "p", "i", bytes(range(32)), bytes(32))
+    assert pf.ProofResult.from_json(pr.to_json()) == pr
+    assert json.loads(pr.to_json())["pre_state_root"] == list(range(32))

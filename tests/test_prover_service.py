@@ -1,0 +1,119 @@
+"""The outer boundary: prover.v1.ProverService over real gRPC, driven by a replay of eigen-zeth's
+client (tools/operator_replay.py, mirroring reference src/prover/provider.rs:243-544).
+CPU tests use a stub backend (protocol / state-machine behaviour only); the GPU test proves for real."""
+import json
+import os
+import sys
+
+import pytest
+
+import oracle_a as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")))
+
+
+class CannedBackend:
+    """returns the reference's canned proof (what DEBUG_PROOF does, src/settlement/worker.rs:49-96)."""
+
+    def __init__(self):
+        self.calls = 0
+        self.fail_next = False
+
+    def final_proof(self, batch_id, recursive_proof, aggregator_addr):
+        self.calls += 1
+        if self.fail_next:
+            self.fail_next = False
+            raise RuntimeError("injected failure")
+        return GOLDEN["proof_json"], GOLDEN["public_input_json"], {}
+
+
+@pytest.fixture()
+def server():
+    from eigen_zeth_b200 import prover_service as ps
+    backend = CannedBackend()
+    servicer = ps.ProverServicer(backend)
+    srv, port = ps.make_server(servicer, "127.0.0.1:0")
+    srv.start()
+    yield "127.0.0.1:%d" % port, backend, servicer
+    srv.stop(0)
+
+
+def test_wire_format_is_prost_compatible():
+    """hand-encoded protobuf bytes of a GenFinalProofRequest (field numbers of prover.proto:13-23,130-135)."""
+    from eigen_zeth_b200 import protocol as pb
+    inner = b"\x0a\x01b" + b"\x12\x02rp" + b"\x1a\x05BN128" + b"\x22\x011"
+    wire = b"\x0a\x01x" + b"\x2a" + bytes([len(inner)]) + inner
+    req = pb.ProverRequest.FromString(wire)
+    assert req.id == "x" and req.WhichOneof("request_type") == "gen_final_proof"
+    assert (req.gen_final_proof.batch_id, req.gen_final_proof.recursive_proof, req.gen_final_proof.curve_name,
+            req.gen_final_proof.aggregator_addr) == ("b", "rp", "BN128", "1")
+    assert req.SerializeToString() == wire
+    # ChunkProof has proof_key = 3 and proof = 2 (prover.proto:107-111)
+    cp = pb.ChunkProof(chunk_id=1, proof_key="k", proof="p")
+    assert cp.SerializeToString() == b"\x08\x01\x12\x01p\x1a\x01k"
+    assert pb.METHOD_PATH == "/prover.v1.ProverService/ProverStream"
+
+
+def test_full_batch_sequence_and_tolerances(server):
+    from operator_replay import OperatorReplay
+    from eigen_zeth_b200 import proof_format as pf
+    addr, backend, _ = server
+    op = OperatorReplay(addr, step_sleep=0.0)
+    res, t = op.execute(block_number=7)
+    assert res.block_number == 7 and len(res.pre_state_root) == 32 and len(res.post_state_root) == 32
+    assert pf.parse_proof(res.proof) == o.parse_proof(GOLDEN["proof_json"])
+    assert pf.ProofResult.from_json(res.to_json()) == res
+    # replay of the same batch id (client resume path) is served from the cache, bit-identical
+    res1, _ = op.execute(block_number=8, batch_id="fixed-batch")
+    calls = backend.calls
+    res2, _ = op.execute(block_number=8, batch_id="fixed-batch")
+    assert backend.calls == calls and res2 == res1
+    # GetStatus is answered in-stream and does not disturb the sequence
+    st = op.get_status()
+    assert st.prover_status.version_server and st.prover_status.number_of_cores > 0
+    assert st.prover_status.last_computed_request_id
+    op.close()
+
+
+def test_errors_keep_the_stream_open(server):
+    from operator_replay import OperatorReplay
+    addr, backend, _ = server
+    op = OperatorReplay(addr, step_sleep=0.0, curve="BLS12381")
+    with pytest.raises(RuntimeError, match="unsupported curve"):
+        op.execute(1)
+    op.curve = "BN128"
+    backend.fail_next = True
+    with pytest.raises(RuntimeError, match="injected failure"):
+        op.execute(2)
+    res, _ = op.execute(3)          # same stream still works: COMPLETED_ERROR never drops it
+    assert res.block_number == 3
+    op.close()
+
+
+@pytest.mark.gpu
+def test_service_proves_on_gpu_and_verifies():
+    from operator_replay import OperatorReplay
+    import eigen_zeth_b200 as z
+    from eigen_zeth_b200 import proof_format as pf, prover_service as ps
+    backend = ps.GpuGroth16Backend(log_n=12)
+    srv, port = ps.make_server(ps.ProverServicer(backend), "127.0.0.1:0")
+    srv.start()
+    try:
+        op = OperatorReplay("127.0.0.1:%d" % port, step_sleep=0.0)
+        seen = set()
+        for k in (1, 2):
+            res, t = op.execute(k, batch_id="batch-%d" % k)
+            proof = pf.proof_from_json(res.proof)
+            pub = pf.public_input_from_json(res.public_input)
+            assert z.groth16_verify(backend.vk, proof, pub)
+            A, B, C = o.parse_proof(res.proof)
+            assert o.g1_is_on_curve(A) and o.g2_is_on_curve(B) and o.g1_is_on_curve(C)
+            seen.add(res.proof)
+            res_again, _ = op.execute(k, batch_id="batch-%d" % k)
+            assert res_again.proof == res.proof
+        assert len(seen) == 2
+        op.close()
+    finally:
+        srv.stop(0)
