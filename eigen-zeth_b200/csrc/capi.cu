@@ -197,7 +197,12 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     if ((rc = coset_tables(ctx, log_n, &t))) return rc;
     post_scale = t->ninv.p;
   }
+  if (!ctx->msm.flag.p) {
+    ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
+  }
   NttPassArgs a{};
+  a.flag = (uint32_t*)ctx->msm.flag.p;
   a.stage_tw = inverse ? ctx->stage_inv.p : ctx->stage_fwd.p;
   a.tw_lo = d->tw_lo.p;
   a.tw_lo_bits = d->lo_bits;
@@ -255,8 +260,15 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
 }
 
 // ---------------------------------------------------------------- MSM glue
-static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b) {
+static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, bool second_set = false) {
   MsmScratch& s = ctx->msm;
+  if (!s.flag.p) {
+    ZKB_CUDA(ctx, s.flag.ensure(16));
+    ZKB_CUDA(ctx, cudaMemsetAsync(s.flag.p, 0, 16, ctx->stream));
+  }
+  if (second_set) ZKB_CUDA(ctx, s.buckets2.ensure(p.n_buckets * p.point_bytes));
+  b->buckets2 = s.buckets2.p;
+  b->flag = (uint32_t*)s.flag.p;
   ZKB_CUDA(ctx, s.keys_in.ensure(p.m * 4));
   ZKB_CUDA(ctx, s.vals_in.ensure(p.m * 4));
   ZKB_CUDA(ctx, s.keys_out.ensure(p.m * 4));
@@ -291,11 +303,28 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b) {
   return ZKB_OK;
 }
 
-int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
-             void* d_out_affine) {
+static int msm_prepare(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t n) {
   if (!b || b->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "bases belong to another device");
   if (first > b->n || n > b->n - first) return set_error(ctx, ZKB_EINVAL, "MSM range exceeds the bases");
-  if (n >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "MSM larger than 2^31 - 1 points");
+  if (b->n >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "MSM larger than 2^31 - 1 points");
+  return ZKB_OK;
+}
+
+static int msm_profile_events(zkb_ctx* ctx, MsmBuffers* buf) {
+  ctx->msm_ev_valid = false;
+  if (ctx->msm_profile) {
+    for (int i = 0; i < 6; i++)
+      if (!ctx->msm_ev[i]) ZKB_CUDA(ctx, cudaEventCreate(&ctx->msm_ev[i]));
+    buf->ev = ctx->msm_ev;
+    ctx->msm_ev_valid = true;
+  }
+  return ZKB_OK;
+}
+
+int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
+             void* d_out_affine) {
+  int rc = msm_prepare(ctx, b, first, n);
+  if (rc) return rc;
   const size_t aff = b->is_g2 ? 128 : 64;
   if (n == 0) {
     ZKB_CUDA(ctx, cudaMemsetAsync(d_out_affine, 0, aff, ctx->stream));
@@ -303,20 +332,76 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
   }
   MsmPlan p = msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
   MsmBuffers buf;
-  int rc = ensure_msm_buffers(ctx, p, &buf);
-  if (rc) return rc;
+  if ((rc = ensure_msm_buffers(ctx, p, &buf))) return rc;
   buf.result_affine = d_out_affine;
-  ctx->msm_ev_valid = false;
-  if (ctx->msm_profile) {
-    for (int i = 0; i < 6; i++)
-      if (!ctx->msm_ev[i]) ZKB_CUDA(ctx, cudaEventCreate(&ctx->msm_ev[i]));
-    buf.ev = ctx->msm_ev;
-    ctx->msm_ev_valid = true;
-  }
+  if ((rc = msm_profile_events(ctx, &buf))) return rc;
   ctx->launches += 8;   // digits, count_valid, L1, L2, finish, bucket_reduce, window_sum, horner
-  const char* base_ptr = reinterpret_cast<const char*>(b->d_pts) + first * aff;
-  if (b->is_g2) msm_run_g2(p, buf, d_scalars, n, base_ptr, ctx->stream);
-  else msm_run_g1(p, buf, d_scalars, n, base_ptr, ctx->stream);
+  // values index the whole base array: the sub-range starts at `first`
+  msm_digits_and_sort(p, buf, d_scalars, n, uint32_t(first), ctx->stream);
+  if (b->is_g2) {
+    msm_accumulate_g2(p, buf, b->d_pts, buf.buckets, ctx->stream);
+    msm_tail_g2(p, buf, ctx->stream);
+  } else {
+    msm_accumulate_g1(p, buf, b->d_pts, buf.buckets, ctx->stream);
+    msm_tail_g1(p, buf, ctx->stream);
+  }
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
+                  uint64_t n, void* d_out_affine) {
+  int rc = msm_prepare(ctx, b, first, n);
+  if (rc) return rc;
+  const size_t aff = b->is_g2 ? 128 : 64;
+  if (n == 0) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(d_out_affine, 0, aff, ctx->stream));
+    return ZKB_OK;
+  }
+  uint32_t chunks = ctx->msm_host_chunks > 0 ? uint32_t(ctx->msm_host_chunks) : (n >= (1ull << 20) ? 4 : 1);
+  if (chunks > 16) chunks = 16;
+  // one window width for the whole MSM so that every chunk fills the same bucket array
+  MsmPlan whole = msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
+  const uint64_t per = (n + chunks - 1) / chunks;
+  MsmPlan p = msm_make_plan(per, b->is_g2, whole.c, ctx->sm_count);
+  MsmBuffers buf;
+  if ((rc = ensure_msm_buffers(ctx, p, &buf, chunks > 1))) return rc;
+  buf.result_affine = d_out_affine;
+  ZKB_CUDA(ctx, cudaMemsetAsync(buf.flag, 0, 16, ctx->stream));   // flags raised by earlier *_dev calls are stale
+  ZKB_CUDA(ctx, ctx->io_a.ensure(n * 32 + 32));
+  if (!ctx->copy_stream) ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (uint32_t k = 0; k < chunks; k++)
+    if (!ctx->copy_ev[k]) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[k], cudaEventDisableTiming));
+  // the copy stream must not overwrite io_a while earlier work on the main stream still reads it
+  ZKB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+  for (uint32_t k = 0; k < chunks; k++) {
+    uint64_t off = uint64_t(k) * per;
+    if (off >= n) { chunks = k; break; }
+    uint64_t cnt = n - off < per ? n - off : per;
+    ZKB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->io_a.p + off * 32, h_scalars + off * 32, cnt * 32,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+    ZKB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+  }
+  for (uint32_t k = 0; k < chunks; k++) {
+    uint64_t off = uint64_t(k) * per;
+    uint64_t cnt = n - off < per ? n - off : per;
+    MsmPlan pk = cnt == per ? p : msm_make_plan(cnt, b->is_g2, whole.c, ctx->sm_count);
+    pk.sort_temp_bytes = p.sort_temp_bytes;
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+    msm_digits_and_sort(pk, buf, (char*)ctx->io_a.p + off * 32, cnt, uint32_t(first + off), ctx->stream);
+    void* target = k == 0 ? buf.buckets : buf.buckets2;
+    if (b->is_g2) msm_accumulate_g2(pk, buf, b->d_pts, target, ctx->stream);
+    else msm_accumulate_g1(pk, buf, b->d_pts, target, ctx->stream);
+    if (k) {
+      if (b->is_g2) msm_merge_g2(pk, buf.buckets, buf.buckets2, ctx->stream);
+      else msm_merge_g1(pk, buf.buckets, buf.buckets2, ctx->stream);
+    }
+    ctx->launches += 5 + (k ? 1 : 0);
+  }
+  if (b->is_g2) msm_tail_g2(p, buf, ctx->stream);
+  else msm_tail_g1(p, buf, ctx->stream);
+  ctx->launches += 3;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -549,6 +634,11 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
   for (DevBuf* b : all) b->release();
   for (int i = 0; i < 6; i++)
     if (ctx->msm_ev[i]) cudaEventDestroy(ctx->msm_ev[i]);
+  for (int i = 0; i < 16; i++)
+    if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  ctx->msm.buckets2.release();
+  ctx->msm.flag.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -567,6 +657,11 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
   if (!std::strcmp(key, "msm_window")) {
     if (value < 0 || value > 20 || value == 1) return set_error(ctx, ZKB_EINVAL, "msm_window must be 0 or 2..20");
     ctx->msm_window = value;
+    return ZKB_OK;
+  }
+  if (!std::strcmp(key, "msm_host_chunks")) {
+    if (value < 0 || value > 16) return set_error(ctx, ZKB_EINVAL, "msm_host_chunks must be 0..16");
+    ctx->msm_host_chunks = value;
     return ZKB_OK;
   }
   if (!std::strcmp(key, "msm_profile")) {
@@ -615,16 +710,30 @@ int zkb_fr_ntt(zkb_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, int cos
   if (!data) return set_error(ctx, ZKB_EINVAL, "null buffer");
   if (log_n < 1 || log_n > 28) return set_error(ctx, ZKB_EINVAL, "log_n must be in [1, 28]");
   uint64_t n = 1ull << log_n;
-  if (!all_canonical_fr(data, n)) return set_error(ctx, ZKB_EINVAL, "non-canonical Fr element");
   {
     ZKB_ENTER(ctx);
     ZKB_CUDA(ctx, ctx->io_a.ensure(n * 32));
+    ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
     ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, data, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   }
-  int rc = zkb_fr_ntt_dev(ctx, ctx->io_a.p, ctx->io_a.p, log_n, inverse, coset, 0);
+  // out of place on the device so that a rejected input leaves the caller's buffer untouched
+  int rc;
+  {
+    ZKB_ENTER(ctx);
+    ZKB_CUDA(ctx, ctx->io_b.ensure(n * 32));
+  }
+  rc = zkb_fr_ntt_dev(ctx, ctx->io_a.p, ctx->io_b.p, log_n, inverse, coset, 0);
   if (rc) return rc;
   ZKB_ENTER(ctx);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(data, ctx->io_a.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t flag = 0;
+  ZKB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag & 1) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
+    return set_error(ctx, ZKB_EINVAL, "non-canonical Fr element");
+  }
+  ZKB_CUDA(ctx, cudaMemcpyAsync(data, ctx->io_b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;
 }
@@ -753,15 +862,21 @@ static int msm_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint
   ZKB_ENTER(ctx);
   if (!b || !out || (!scalars && n)) return set_error(ctx, ZKB_EINVAL, "null argument");
   if (b->is_g2 != want_g2) return set_error(ctx, ZKB_EINVAL, "bases are of the other group");
-  if (!all_canonical_fr(scalars, n)) return set_error(ctx, ZKB_EINVAL, "non-canonical scalar");
   const size_t aff = want_g2 ? 128 : 64;
-  ZKB_CUDA(ctx, ctx->io_a.ensure(n * 32 + 32));
   ZKB_CUDA(ctx, ctx->io_c.ensure(256));
-  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = msm_exec(ctx, b, first, ctx->io_a.p, n, ctx->io_c.p);
+  int rc = msm_exec_host(ctx, b, first, scalars, n, ctx->io_c.p);
   if (rc) return rc;
+  // result and the canonicity flag raised by the digit kernel come back together
+  uint32_t flag = 0;
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_c.p, aff, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->msm.flag.p)
+    ZKB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag & 1) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
+    std::memset(out, 0, aff);
+    return set_error(ctx, ZKB_EINVAL, "non-canonical scalar");
+  }
   return ZKB_OK;
 }
 int zkb_msm_g1(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,

@@ -53,6 +53,7 @@ struct CosetTables {        // per log_n
 };
 
 struct MsmScratch {
+  DevBuf buckets2, flag;
   DevBuf keys_in, vals_in, keys_out, vals_out, sort_temp, m_valid, buckets, part1_keys,
       part1_pts, part2_keys, part2_pts, group_sums, window_sums, result_xyzz, result_affine;
 };
@@ -75,6 +76,9 @@ struct zkb_ctx {
   int64_t msm_window = 0;
   int64_t ntt_full_twiddles = 0;
   int64_t msm_profile = 0;
+  int64_t msm_host_chunks = 0;             // 0 = auto
+  cudaStream_t copy_stream = nullptr;      // H2D of scalar chunks, overlapped with compute
+  cudaEvent_t copy_ev[16] = {};
   cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool msm_ev_valid = false;
   uint64_t launches = 0;                   // kernels of this library launched so far
@@ -113,6 +117,9 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
 int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out);
 int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
              void* d_out_affine);
+// host scalars: H2D in chunks on the copy stream, overlapped with the per-chunk MSM front half
+int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
+                  uint64_t n, void* d_out_affine);
 int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g2, void* d_out);
 int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
                           uint8_t* out);

@@ -452,11 +452,7 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     bool ok = HFr::lt_mod(w);
     std::memcpy(w, s, 32);
     ok = ok && HFr::lt_mod(w);
-    for (uint64_t i = 0; ok && i < m; i++) {
-      std::memcpy(w, witness + 32 * i, 32);
-      ok = HFr::lt_mod(w);
-    }
-    if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in witness / r / s");
+    if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical r / s");
   }
   cudaStream_t st = ctx->stream;
   enum { E_START, E_H2D, E_SPMV, E_NTT, E_A, E_B1, E_B2, E_L, E_H, E_END, E_COUNT };
@@ -464,8 +460,12 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
   for (int i = 0; i < E_COUNT; i++) ZKB_CUDA(ctx, cudaEventCreate(&ev[i]));
   auto mark = [&](int i) { cudaEventRecord(ev[i], st); };
   int rc = ZKB_OK;
+  cudaError_t e0 = cudaSuccess;
+  uint32_t bad_flag = 0;
   do {
     mark(E_START);
+    if ((e0 = ctx->msm.flag.ensure(16)) != cudaSuccess) { rc = cuda_fail(ctx, e0, "flag"); break; }
+    cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);   // the MSM digit kernels flag a non-canonical witness
     cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES, r, 32, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES + 32, s, 32, cudaMemcpyHostToDevice, st);
@@ -507,10 +507,17 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     if (intermediates_opt)
       cudaMemcpyAsync(intermediates_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
     if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad_flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
       rc = cuda_fail(ctx, e, "groth16 prove");
+      break;
+    }
+    if (bad_flag & 1) {
+      cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);
+      std::memset(proof_out, 0, ZKB_PROOF_BYTES);
+      rc = set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in the witness");
       break;
     }
     if (timings_opt) {

@@ -29,6 +29,8 @@ struct MsmBuffers {
   void* sort_temp;
   uint64_t* m_valid;
   void* buckets;            // n_buckets XYZZ
+  void* buckets2;           // second bucket set (chunked MSM), may be null
+  uint32_t* flag;           // bit 0: a scalar was not canonical
   uint32_t* part1_keys;     // 2 * l1_threads
   void* part1_pts;
   uint32_t* part2_keys;     // 2 * l2_threads
@@ -41,12 +43,18 @@ struct MsmBuffers {
 };
 
 MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count);
+// scalars[0..n) -> sorted (key, value) stream; values carry idx_base + i.  Non-canonical scalars
+// (>= r) raise bit 0 of *d_flag.
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
-                         cudaStream_t s);
-void msm_run_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
-                const void* d_bases, cudaStream_t s);
-void msm_run_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
-                const void* d_bases, cudaStream_t s);
+                         uint32_t idx_base, cudaStream_t s);
+void msm_accumulate_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
+                       cudaStream_t s);
+void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
+                       cudaStream_t s);
+void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
+void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
+void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
+void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
 void msm_bases_to_mont_g1(void* d_pts, uint64_t n, cudaStream_t s);
 void msm_bases_to_mont_g2(void* d_pts, uint64_t n, cudaStream_t s);
 void msm_sum_affine_g1(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s);

@@ -11,12 +11,26 @@ namespace zkb {
 // ---------------------------------------------------------------- 1. digits
 __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t c,
                                   uint32_t nwin, uint32_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals, uint32_t idx_base) {
+                                  uint32_t* __restrict__ vals, uint32_t idx_base,
+                                  uint32_t* __restrict__ flag) {
   uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
   uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
   uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+  {  // canonicity: s < r  (compare from the top limb)
+    const uint32_t rmod[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                              0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    bool lt = false, decided = false;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      if (!decided && s[k] != rmod[k]) {
+        lt = s[k] < rmod[k];
+        decided = true;
+      }
+    }
+    if (!lt) atomicOr(flag, 1u);
+  }
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (1u << c) - 1;
   const uint32_t sentinel = nwin * half;
@@ -93,12 +107,12 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count) {
 
 
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
-                         cudaStream_t s) {
+                         uint32_t idx_base, cudaStream_t s) {
   if (b.ev) cudaEventRecord(b.ev[0], s);
   uint32_t blocks = uint32_t((n + 255) / 256);
   if (blocks)
     msm_digits_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, p.c,
-                                             p.nwin, b.keys_in, b.vals_in, 0);
+                                             p.nwin, b.keys_in, b.vals_in, idx_base, b.flag);
   if (b.ev) cudaEventRecord(b.ev[1], s);
   size_t temp = p.sort_temp_bytes;
   cub::DeviceRadixSort::SortPairs(b.sort_temp, temp, (const uint32_t*)b.keys_in, b.keys_out,

@@ -245,25 +245,52 @@ __global__ void msm_sum_affine_kernel(const Affine<F>* pts, uint32_t n, Affine<F
   a.store(out);
 }
 
+// main[j] += part[j] for every bucket (merging the bucket sets of point chunks)
 template <class F>
-void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
-                      const void* d_bases, cudaStream_t s) {
+__global__ void __launch_bounds__(128) msm_bucket_merge_kernel(XYZZ<F>* __restrict__ main_b,
+                                                               const XYZZ<F>* __restrict__ part,
+                                                               uint64_t n_buckets) {
+  uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (j >= n_buckets) return;
+  XYZZ<F> a = XYZZ<F>::load(part + j);
+  if (a.is_inf()) return;
+  XYZZ<F> m = XYZZ<F>::load(main_b + j);
+  m.add(a);
+  m.store(main_b + j);
+}
+
+// sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first)
+template <class F>
+void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases,
+                      void* bucket_target, cudaStream_t s) {
   using P = XYZZ<F>;
-  msm_digits_and_sort(p, b, d_scalars, n, s);
-  cudaMemsetAsync(b.buckets, 0, p.n_buckets * sizeof(P), s);
+  cudaMemsetAsync(bucket_target, 0, p.n_buckets * sizeof(P), s);
   msm_accumulate_l1_kernel<F><<<(p.l1_threads + 127) / 128, 128, 0, s>>>(
       b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
-      reinterpret_cast<P*>(b.buckets), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
+      reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
       p.l1_threads);
   if (b.ev) cudaEventRecord(b.ev[3], s);
   msm_accumulate_l2_kernel<F><<<(p.l2_threads + 127) / 128, 128, 0, s>>>(
       b.part1_keys, reinterpret_cast<const P*>(b.part1_pts), 2 * p.l1_threads, p.l2_len,
-      reinterpret_cast<P*>(b.buckets), b.part2_keys, reinterpret_cast<P*>(b.part2_pts),
+      reinterpret_cast<P*>(bucket_target), b.part2_keys, reinterpret_cast<P*>(b.part2_pts),
       p.l2_threads);
   msm_finish_kernel<F><<<(2 * p.l2_threads + 127) / 128, 128, 0, s>>>(
       b.part2_keys, reinterpret_cast<const P*>(b.part2_pts), 2 * p.l2_threads,
-      reinterpret_cast<P*>(b.buckets));
+      reinterpret_cast<P*>(bucket_target));
   if (b.ev) cudaEventRecord(b.ev[4], s);
+}
+
+template <class F>
+void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
+  using P = XYZZ<F>;
+  msm_bucket_merge_kernel<F><<<uint32_t((p.n_buckets + 127) / 128), 128, 0, s>>>(
+      reinterpret_cast<P*>(main_buckets), reinterpret_cast<const P*>(part_buckets), p.n_buckets);
+}
+
+// bucket sums -> one point (Montgomery XYZZ + canonical affine)
+template <class F>
+void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
+  using P = XYZZ<F>;
   msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
       reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
       reinterpret_cast<P*>(b.group_sums));
@@ -275,7 +302,6 @@ void msm_run_t(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uin
                                         reinterpret_cast<Affine<F>*>(b.result_affine));
   if (b.ev) cudaEventRecord(b.ev[5], s);
 }
-
 
 template <class F>
 void msm_bases_to_mont_t(void* d_pts, uint64_t n, cudaStream_t s) {

@@ -62,6 +62,18 @@ __device__ __forceinline__ Fr tw_load(const uint4* tw, int b, int i) {
   return x;
 }
 
+__device__ __forceinline__ bool fr_is_canonical(const Fr& x) {
+  bool lt = false, decided = false;
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    if (!decided && x.v[k] != FrParams::mod(k)) {
+      lt = x.v[k] < FrParams::mod(k);
+      decided = true;
+    }
+  }
+  return lt;
+}
+
 // decimation-in-frequency butterfly
 __device__ __forceinline__ void bfly(Fr& a, Fr& b, const Fr& w) {
   Fr t = a - b;
@@ -153,7 +165,10 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
       if (!FINAL) idx = base + uint64_t(t) * p.S + c;
       else idx = ((uint64_t(c_base + c) << mid_bits) + mid) * (1u << k) + t;
       x = Fr::load_nc(in + idx * 32);
-      if (!p.mont_in) x = x.to_mont();
+      if (!p.mont_in) {
+        if (!fr_is_canonical(x)) atomicOr(p.flag, 1u);
+        x = x.to_mont();
+      }
       if (p.pre_scale) x = x * Fr::load_nc(reinterpret_cast<const char*>(p.pre_scale) + idx * 32);
     }
     sm_store(data, c >> gbits, ((c & ((1 << gbits) - 1)) << k) | t, x);

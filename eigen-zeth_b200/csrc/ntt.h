@@ -25,6 +25,7 @@ struct NttPassArgs {
   uint32_t first_digit_bits;  // final mode: width of K_0 (0 when P == 1)
   uint32_t n_row_digits;
   uint32_t row_digit_bits[4];
+  uint32_t* flag;          // bit 0 raised when a canonical-form input (mont_in == 0) is >= r
   int mont_in;             // 0: input is canonical integers, convert while loading
   int mont_out;            // 0: convert the result back to canonical integers while storing
 };
