@@ -317,6 +317,33 @@ def main():
             line["groth16_2^22"] = {"error": str(ex)}
         cpu, cpu_out = cpu_baseline_msm()
         line["cpu_baseline"] = cpu
+    elif not args.no_extras and world > 1:
+        # ---- Groth16 2^22 with every MSM sharded by point range over the ranks
+        try:
+            from eigen_zeth_b200.sharding import groth16_prove_sharded
+            glog = 22
+            pk = ctx.pk_synthetic_shard(glog, SEED + 4, rank, world)
+            w = z.synthetic_witness(glog, (5).to_bytes(32, "little"), (7).to_bytes(32, "little"))
+            wt = torch.frombuffer(bytearray(w), dtype=torch.uint8).pin_memory()
+            r, s = (11).to_bytes(32, "little"), (13).to_bytes(32, "little")
+            best = None
+            for i in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                proof, tm = groth16_prove_sharded(ctx, pk, wt.data_ptr(), r, s, world)
+                barrier()
+                dt = torch.tensor([time.perf_counter() - t0], device=dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                if i and (best is None or float(dt.item()) < best[0]):
+                    best = (float(dt.item()), tm)
+            if rank == 0:
+                ok = z.groth16_verify(pk.vk, proof, w[32:64])
+                line["groth16_2^22"] = {"prove_ms_e2e": best[0] * 1e3, "rank0_stage_ms": best[1], "pairing_verified": bool(ok),
+                                        "sharding": "every MSM by point range over %d ranks; NTT phase replicated" % world}
+            pk.free()
+        except Exception as ex:
+            line["groth16_2^22"] = {"error": str(ex)}
+        line["cpu_baseline"] = None
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

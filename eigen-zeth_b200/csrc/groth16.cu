@@ -35,6 +35,10 @@ struct zkb_pk {
   void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_z = nullptr, *d_zm = nullptr;
   void* d_results = nullptr;         // msm_a 64 | msm_b1 64 | msm_b2 128 | msm_l 64 | msm_h 64
   void* d_proof = nullptr;           // 256 B + r,s staging (64 B)
+  // point-range shard held by this key: query q covers [qfirst[q], qfirst[q] + qcount[q]) of the
+  // full query (q = 0 a, 1 b_g1, 2 b_g2, 3 l, 4 h); world == 1 means the whole key
+  uint32_t rank = 0, world = 1;
+  uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
 };
 
 namespace zkb {
@@ -215,8 +219,8 @@ static cudaError_t upload_vec(const std::vector<T>& v, T** d, cudaStream_t s) {
   return cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
-static int make_query(zkb_ctx* ctx, const std::vector<uint64_t>& scalars_canon, uint64_t count,
-                      int is_g2, zkb_bases** out) {
+static int make_query(zkb_ctx* ctx, const std::vector<uint64_t>& scalars_canon, uint64_t first,
+                      uint64_t count, int is_g2, zkb_bases** out) {
   zkb_bases* b = new (std::nothrow) zkb_bases();
   if (!b) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
   b->device = ctx->device;
@@ -229,7 +233,7 @@ static int make_query(zkb_ctx* ctx, const std::vector<uint64_t>& scalars_canon, 
   }
   *out = b;
   ZKB_CUDA(ctx, ctx->io_a.ensure(count * 32 + 32));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars_canon.data(), count * 32,
+  ZKB_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars_canon.data() + 4 * first, count * 32,
                                 cudaMemcpyHostToDevice, ctx->stream));
   int rc = bases_from_scalars(ctx, ctx->io_a.p, count, is_g2, b->d_pts);
   if (rc) return rc;
@@ -305,11 +309,17 @@ int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1
 
 int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
                      uint8_t vk_out[ZKB_VK_BYTES]) {
+  return zkb_pk_synthetic_shard(ctx, log_n, seed, 0, 1, out, vk_out);
+}
+
+int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
+                           zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]) {
   if (!ctx) return ZKB_EINVAL;
   BusyGuard guard(ctx);
   if (!guard.ok) return ZKB_EBUSY;
   if (!out || !vk_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   if (log_n < 3 || log_n > 26) return set_error(ctx, ZKB_EINVAL, "log_n must be in [3, 26]");
+  if (world == 0 || rank >= world || world > 64) return set_error(ctx, ZKB_EINVAL, "bad rank / world");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   zkb_pk* pk = new (std::nothrow) zkb_pk();
   if (!pk) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
@@ -322,6 +332,14 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
     pk->n = n;
     pk->m = m;
     pk->ncons = cs.ncons;
+    pk->rank = rank;
+    pk->world = world;
+    const uint64_t qlen[5] = {m, m, m, m - 2, n - 1};
+    for (int q = 0; q < 5; q++) {
+      uint64_t base = qlen[q] / world, rem = qlen[q] % world;
+      pk->qfirst[q] = rank * base + (rank < rem ? rank : rem);
+      pk->qcount[q] = base + (rank < rem ? 1 : 0);
+    }
     host::Xoshiro256ss rng(seed);
     HFr tau = rng.fr(), alpha = rng.fr(), beta = rng.fr(), gamma = rng.fr(), delta = rng.fr();
     // Lagrange basis at tau
@@ -363,31 +381,31 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
     // scalars (canonical) for every query; one reusable staging vector
     std::vector<uint64_t> sc(4 * n);
     for (uint64_t i = 0; i < m; i++) canon_into(u[i], sc, i);
-    if ((rc = make_query(ctx, sc, m, 0, &pk->a_query))) throw rc;
+    if ((rc = make_query(ctx, sc, pk->qfirst[0], pk->qcount[0], 0, &pk->a_query))) throw rc;
     for (uint64_t i = 0; i < m; i++) canon_into(v[i], sc, i);
-    if ((rc = make_query(ctx, sc, m, 0, &pk->b_g1_query))) throw rc;
-    if ((rc = make_query(ctx, sc, m, 1, &pk->b_g2_query))) throw rc;
+    if ((rc = make_query(ctx, sc, pk->qfirst[1], pk->qcount[1], 0, &pk->b_g1_query))) throw rc;
+    if ((rc = make_query(ctx, sc, pk->qfirst[2], pk->qcount[2], 1, &pk->b_g2_query))) throw rc;
     HFr abc[2];
     for (uint64_t i = 0; i < m; i++) {
       HFr t = beta * u[i] + alpha * v[i] + wv[i];
       if (i < 2) abc[i] = t * gi;
       else canon_into(t * di, sc, i - 2);
     }
-    if ((rc = make_query(ctx, sc, m - 2, 0, &pk->l_query))) throw rc;
+    if ((rc = make_query(ctx, sc, pk->qfirst[3], pk->qcount[3], 0, &pk->l_query))) throw rc;
     HFr tp = zt * di;
     for (uint64_t i = 0; i + 1 < n; i++) {
       canon_into(tp, sc, i);
       tp = tp * tau;
     }
-    if ((rc = make_query(ctx, sc, n - 1, 0, &pk->h_query))) throw rc;
+    if ((rc = make_query(ctx, sc, pk->qfirst[4], pk->qcount[4], 0, &pk->h_query))) throw rc;
     // fixed points: [alpha, beta, delta, ic0, ic1] * G1 and [beta, delta, gamma] * G2
     std::vector<uint64_t> f1(4 * 5), f2(4 * 3);
     canon_into(alpha, f1, 0); canon_into(beta, f1, 1); canon_into(delta, f1, 2);
     canon_into(abc[0], f1, 3); canon_into(abc[1], f1, 4);
     canon_into(beta, f2, 0); canon_into(delta, f2, 1); canon_into(gamma, f2, 2);
     zkb_bases *b1 = nullptr, *b2 = nullptr;
-    if ((rc = make_query(ctx, f1, 5, 0, &b1))) throw rc;
-    if ((rc = make_query(ctx, f2, 3, 1, &b2))) { zkb_bases_free(b1); throw rc; }
+    if ((rc = make_query(ctx, f1, 0, 5, 0, &b1))) throw rc;
+    if ((rc = make_query(ctx, f2, 0, 3, 1, &b2))) { zkb_bases_free(b1); throw rc; }
     cudaError_t e = cudaMalloc(&pk->d_fixed, 3 * 64 + 2 * 128);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pk->d_fixed, b1->d_pts, 3 * 64, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync((char*)pk->d_fixed + 192, b2->d_pts, 2 * 128, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -435,27 +453,12 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
   return ZKB_OK;
 }
 
-int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
-                      const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
-                      uint8_t* intermediates_opt, uint8_t* h_out_opt,
-                      zkb_prove_timings* timings_opt) {
-  if (!ctx) return ZKB_EINVAL;
-  BusyGuard guard(ctx);
-  if (!guard.ok) return ZKB_EBUSY;
-  if (!pk || !witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
-  if (pk->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "proving key lives on another device");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+// phase 1: witness -> the five MSM sums over this key's point ranges (pk->d_results) and h (pk->d_a)
+static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
+                           zkb_prove_timings* timings_opt, uint8_t* h_out_opt, uint8_t* results_out_opt) {
   const uint64_t n = pk->n, m = pk->m;
-  {
-    uint64_t w[4];
-    std::memcpy(w, r, 32);
-    bool ok = HFr::lt_mod(w);
-    std::memcpy(w, s, 32);
-    ok = ok && HFr::lt_mod(w);
-    if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical r / s");
-  }
   cudaStream_t st = ctx->stream;
-  enum { E_START, E_H2D, E_SPMV, E_NTT, E_A, E_B1, E_B2, E_L, E_H, E_END, E_COUNT };
+  enum { E_START, E_H2D, E_SPMV, E_NTT, E_A, E_B1, E_B2, E_L, E_H, E_COUNT };
   cudaEvent_t ev[E_COUNT];
   for (int i = 0; i < E_COUNT; i++) ZKB_CUDA(ctx, cudaEventCreate(&ev[i]));
   auto mark = [&](int i) { cudaEventRecord(ev[i], st); };
@@ -467,8 +470,6 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     if ((e0 = ctx->msm.flag.ensure(16)) != cudaSuccess) { rc = cuda_fail(ctx, e0, "flag"); break; }
     cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);   // the MSM digit kernels flag a non-canonical witness
     cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES, r, 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES + 32, s, 32, cudaMemcpyHostToDevice, st);
     mark(E_H2D);
     const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
     fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
@@ -488,24 +489,20 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     if ((rc = ntt_run(ctx, pk->d_a, pk->d_a, pk->log_n, 1, nullptr, ct->inv_z.p, 0, 1, 0))) break;
     mark(E_NTT);
     char* res = (char*)pk->d_results;
-    if ((rc = msm_exec(ctx, pk->a_query, 0, pk->d_z, m, res))) break;
+    const char* z = (const char*)pk->d_z;
+    if ((rc = msm_exec(ctx, pk->a_query, 0, z + 32 * pk->qfirst[0], pk->qcount[0], res))) break;
     mark(E_A);
-    if ((rc = msm_exec(ctx, pk->b_g1_query, 0, pk->d_z, m, res + 64))) break;
+    if ((rc = msm_exec(ctx, pk->b_g1_query, 0, z + 32 * pk->qfirst[1], pk->qcount[1], res + 64))) break;
     mark(E_B1);
-    if ((rc = msm_exec(ctx, pk->b_g2_query, 0, pk->d_z, m, res + 128))) break;
+    if ((rc = msm_exec(ctx, pk->b_g2_query, 0, z + 32 * pk->qfirst[2], pk->qcount[2], res + 128))) break;
     mark(E_B2);
-    if ((rc = msm_exec(ctx, pk->l_query, 0, (char*)pk->d_z + 64, m - 2, res + 256))) break;
+    if ((rc = msm_exec(ctx, pk->l_query, 0, z + 32 * (2 + pk->qfirst[3]), pk->qcount[3], res + 256))) break;
     mark(E_L);
-    if ((rc = msm_exec(ctx, pk->h_query, 0, pk->d_a, n - 1, res + 320))) break;
+    if ((rc = msm_exec(ctx, pk->h_query, 0, (const char*)pk->d_a + 32 * pk->qfirst[4], pk->qcount[4], res + 320))) break;
     mark(E_H);
-    groth16_assemble_kernel<<<1, 128, 0, st>>>((const uint8_t*)pk->d_results, (const uint8_t*)pk->d_fixed,
-                                               (const uint32_t*)((char*)pk->d_proof + ZKB_PROOF_BYTES),
-                                               (uint8_t*)pk->d_proof);
-    ctx->launches += 6;   // to_mont copy, 3 x SpMV, pointwise, assemble (NTT/MSM count themselves)
-    cudaMemcpyAsync(proof_out, pk->d_proof, ZKB_PROOF_BYTES, cudaMemcpyDeviceToHost, st);
-    mark(E_END);
-    if (intermediates_opt)
-      cudaMemcpyAsync(intermediates_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
+    ctx->launches += 5;   // to_mont copy, 3 x SpMV, pointwise (NTT/MSM count themselves)
+    if (results_out_opt)
+      cudaMemcpyAsync(results_out_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
     if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&bad_flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -516,7 +513,6 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
     }
     if (bad_flag & 1) {
       cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);
-      std::memset(proof_out, 0, ZKB_PROOF_BYTES);
       rc = set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in the witness");
       break;
     }
@@ -525,11 +521,85 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
                     &timings_opt->ms_msm_a, &timings_opt->ms_msm_b1, &timings_opt->ms_msm_b2,
                     &timings_opt->ms_msm_l, &timings_opt->ms_msm_h};
       for (int i = 0; i < 8; i++) cudaEventElapsedTime(f[i], ev[i], ev[i + 1]);
-      cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_END]);
+      cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_H]);
     }
   } while (0);
   for (int i = 0; i < E_COUNT; i++) cudaEventDestroy(ev[i]);
   return rc;
+}
+
+// phase 2: MSM sums in pk->d_results + (r, s) -> proof
+static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[32], const uint8_t s[32],
+                                uint8_t* proof_out, float* ms_opt) {
+  uint64_t w[4];
+  std::memcpy(w, r, 32);
+  bool ok = HFr::lt_mod(w);
+  std::memcpy(w, s, 32);
+  ok = ok && HFr::lt_mod(w);
+  if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical r / s");
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0, e1;
+  ZKB_CUDA(ctx, cudaEventCreate(&e0));
+  ZKB_CUDA(ctx, cudaEventCreate(&e1));
+  cudaEventRecord(e0, st);
+  cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES, r, 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync((char*)pk->d_proof + ZKB_PROOF_BYTES + 32, s, 32, cudaMemcpyHostToDevice, st);
+  groth16_assemble_kernel<<<1, 128, 0, st>>>((const uint8_t*)pk->d_results, (const uint8_t*)pk->d_fixed,
+                                             (const uint32_t*)((char*)pk->d_proof + ZKB_PROOF_BYTES),
+                                             (uint8_t*)pk->d_proof);
+  ctx->launches += 1;
+  cudaMemcpyAsync(proof_out, pk->d_proof, ZKB_PROOF_BYTES, cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess && ms_opt) cudaEventElapsedTime(ms_opt, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "groth16 assemble");
+  return ZKB_OK;
+}
+
+#define ZKB_PK_ENTER(ctx, pk)                                                             \
+  if (!(ctx)) return ZKB_EINVAL;                                                          \
+  BusyGuard guard(ctx);                                                                   \
+  if (!guard.ok) return ZKB_EBUSY;                                                        \
+  if (!(pk)) return set_error(ctx, ZKB_EINVAL, "null proving key");                       \
+  if ((pk)->device != (ctx)->device)                                                      \
+    return set_error(ctx, ZKB_EINVAL, "proving key lives on another device");            \
+  ZKB_CUDA(ctx, cudaSetDevice((ctx)->device));
+
+int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
+                      const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
+                      uint8_t* intermediates_opt, uint8_t* h_out_opt,
+                      zkb_prove_timings* timings_opt) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (pk->world != 1)
+    return set_error(ctx, ZKB_EINVAL, "sharded key: use zkb_groth16_prove_partial + zkb_groth16_assemble");
+  int rc = prove_msm_phase(ctx, pk, witness, timings_opt, h_out_opt, intermediates_opt);
+  if (rc) {
+    std::memset(proof_out, 0, ZKB_PROOF_BYTES);
+    return rc;
+  }
+  float ms = 0;
+  rc = prove_assemble_phase(ctx, pk, r, s, proof_out, &ms);
+  if (!rc && timings_opt) timings_opt->ms_total += ms;
+  return rc;
+}
+
+int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
+                              uint8_t partial_out[ZKB_INTERMEDIATE_BYTES], zkb_prove_timings* timings_opt) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!witness || !partial_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  return prove_msm_phase(ctx, pk, witness, timings_opt, nullptr, partial_out);
+}
+
+int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
+                         const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES]) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!sums || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_results, sums, ZKB_INTERMEDIATE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  return prove_assemble_phase(ctx, pk, r, s, proof_out, nullptr);
 }
 
 }  // extern "C"

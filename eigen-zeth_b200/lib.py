@@ -20,7 +20,8 @@ EXPORTS = [
     "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
-    "zkb_pk_synthetic", "zkb_pk_free", "zkb_pk_query", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_free", "zkb_pk_query",
+    "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
@@ -78,6 +79,9 @@ def load_library() -> C.CDLL:
     lib.zkb_bases_free.restype = None
     if hasattr(lib, "zkb_pk_synthetic"):
         lib.zkb_pk_synthetic.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
+        lib.zkb_pk_synthetic_shard.argtypes = [vp, u32, u64, u32, u32, C.POINTER(vp), vp]
+        lib.zkb_groth16_prove_partial.argtypes = [vp, vp, vp, vp, C.POINTER(ProveTimings)]
+        lib.zkb_groth16_assemble.argtypes = [vp, vp, u8p, u8p, u8p, vp]
         lib.zkb_pk_free.argtypes = [vp]
         lib.zkb_pk_free.restype = None
         lib.zkb_pk_query.argtypes = [vp, i32]
@@ -269,6 +273,29 @@ class Context:
         vk = C.create_string_buffer(VK_BYTES)
         self._check(self.lib.zkb_pk_synthetic(self.h, log_n, seed, C.byref(h), vk))
         return ProvingKey(self, h, vk.raw, log_n)
+
+    def pk_synthetic_shard(self, log_n: int, seed: int, rank: int, world: int) -> ProvingKey:
+        h = C.c_void_p()
+        vk = C.create_string_buffer(VK_BYTES)
+        self._check(self.lib.zkb_pk_synthetic_shard(self.h, log_n, seed, rank, world, C.byref(h), vk))
+        return ProvingKey(self, h, vk.raw, log_n)
+
+    def groth16_prove_partial(self, pk: ProvingKey, witness):
+        """-> (384-byte partial MSM sums over this key's point ranges, timings)"""
+        out = C.create_string_buffer(INTERMEDIATE_BYTES)
+        t = ProveTimings()
+        if isinstance(witness, (bytes, bytearray)):
+            wbuf = C.create_string_buffer(bytes(witness), len(witness))
+            wptr = C.cast(wbuf, C.c_void_p)
+        else:
+            wptr = C.c_void_p(int(witness))
+        self._check(self.lib.zkb_groth16_prove_partial(self.h, pk.handle, wptr, out, C.byref(t)))
+        return out.raw, t.as_dict()
+
+    def groth16_assemble(self, pk: ProvingKey, sums: bytes, r: bytes, s: bytes) -> bytes:
+        proof = C.create_string_buffer(PROOF_BYTES)
+        self._check(self.lib.zkb_groth16_assemble(self.h, pk.handle, bytes(sums), r, s, proof))
+        return proof.raw
 
     def groth16_prove(self, pk: ProvingKey, witness, r: bytes, s: bytes, want_intermediates=False, want_h=False):
         """witness: bytes or raw host pointer (int). returns (proof, intermediates|None, h|None, timings)."""

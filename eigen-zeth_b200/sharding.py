@@ -43,3 +43,32 @@ def sharded_msm(local_msm: Callable[[int, int], "object"], point_sum: Callable[[
     first, count = shard_range(n, world, rank)
     partial = local_msm(first, count)
     return point_sum(gather_partials(partial, world))
+
+
+# slot layout of the 384-byte MSM-sum block (include/zkb.h): (offset, size, is_g2)
+SLOTS = ((0, 64, False), (64, 64, False), (128, 128, True), (256, 64, False), (320, 64, False))
+
+
+def combine_partial_sums(partials, point_sum: Callable[[bytes, bool], bytes]) -> bytes:
+    """partials: list of 384-byte blocks (one per rank) -> slot-wise sums (384 bytes).
+    point_sum(points_bytes, is_g2) adds affine points (zkb_g1_sum / zkb_g2_sum on the GPU)."""
+    out = bytearray(384)
+    for off, size, g2 in SLOTS:
+        pts = b"".join(bytes(p[off:off + size]) for p in partials)
+        out[off:off + size] = point_sum(pts, g2)
+    return bytes(out)
+
+
+def groth16_prove_sharded(ctx, pk, witness, r: bytes, s: bytes, world: int):
+    """One proof with every MSM sharded by point range over `world` ranks (each rank's `pk` holds
+    its ranges, zkb_pk_synthetic_shard).  Every rank returns the same proof bytes."""
+    import torch
+    partial, timings = ctx.groth16_prove_partial(pk, witness)
+    if world == 1:
+        parts = [partial]
+    else:
+        dev = torch.device("cuda", ctx.device)
+        t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(dev)
+        parts = [bytes(row.cpu().numpy()) for row in gather_partials(t, world)]
+    sums = combine_partial_sums(parts, lambda pts, g2: ctx.point_sum(pts, g2=g2))
+    return ctx.groth16_assemble(pk, sums, r, s), timings

@@ -94,6 +94,10 @@ int zkb_g2_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out);
  * toxic waste from xoshiro256**(seed); queries are computed on the GPU and stay resident. */
 int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
                      uint8_t vk_out[ZKB_VK_BYTES]);
+/* the same key, but only the point range of rank `rank` out of `world` of every query stays on
+ * this GPU (one process per GPU; the MSM partial sums are combined above this layer) */
+int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
+                           zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]);
 void zkb_pk_free(zkb_pk* pk);
 /* borrowed handle to one query of the key: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 l_query,
  * 4 h_query (ark-groth16 ProvingKey field names); valid until zkb_pk_free; do not free it */
@@ -110,6 +114,13 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
                       const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
                       uint8_t* intermediates_opt, uint8_t* h_out_opt,
                       zkb_prove_timings* timings_opt);
+/* multi-GPU composition: every rank computes the five MSM sums over ITS point ranges
+ * (msm_a 64 | msm_b1 64 | msm_b2 128 | msm_l 64 | msm_h 64); the ranks' partials are added slot by
+ * slot (zkb_g1_sum / zkb_g2_sum after an all-gather) and any rank assembles the proof */
+int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
+                              uint8_t partial_out[ZKB_INTERMEDIATE_BYTES], zkb_prove_timings* timings_opt);
+int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
+                         const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES]);
 /* CPU pairing check e(A,B) = e(alpha,beta) e(ic0 + x*ic1, gamma) e(C,delta); 0 = valid,
  * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
 int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],

@@ -80,3 +80,28 @@ def test_prove_large_pairing_verified(ctx, zkb, log_n):
     assert not zkb.groth16_verify(pk.vk, proof_bad, wit[32:64])
     print("prove 2^%d: %s" % (log_n, t))
     pk.free()
+
+
+@pytest.mark.parametrize("log_n,world", [(6, 2), (10, 3), (14, 4)])
+def test_sharded_prove_equals_single_gpu(ctx, zkb, log_n, world):
+    """point-range sharding of every MSM, emulated on one GPU: the `world` sharded
+    keys produce partial sums whose slot-wise sum assembles to the same proof bytes."""
+    from eigen_zeth_b200.sharding import combine_partial_sums
+    seed = 0x5EED0004 + log_n
+    w0, w1, r, s = _inputs(seed + 3)
+    wit = zkb.synthetic_witness(log_n, w0, w1)
+    pk = ctx.pk_synthetic(log_n, seed)
+    want, inter, _, _ = ctx.groth16_prove(pk, wit, r, s, want_intermediates=True)
+    parts = []
+    for rank in range(world):
+        spk = ctx.pk_synthetic_shard(log_n, seed, rank, world)
+        assert spk.vk == pk.vk
+        with pytest.raises(zkb.ZkbError):
+            ctx.groth16_prove(spk, wit, r, s)          # a sharded key cannot prove alone
+        part, _ = ctx.groth16_prove_partial(spk, wit)
+        parts.append(part)
+        last = spk
+    sums = combine_partial_sums(parts, lambda pts, g2: ctx.point_sum(pts, g2=g2))
+    assert sums == inter
+    assert ctx.groth16_assemble(last, sums, r, s) == want
+    assert zkb.groth16_verify(pk.vk, want, wit[32:64])
