@@ -281,7 +281,7 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, boo
   ZKB_CUDA(ctx, s.part2_keys.ensure(2ull * p.l2_threads * 4));
   ZKB_CUDA(ctx, s.part2_pts.ensure(2ull * p.l2_threads * p.point_bytes));
   ZKB_CUDA(ctx, s.group_sums.ensure(uint64_t(p.n_groups) * p.point_bytes));
-  ZKB_CUDA(ctx, s.window_sums.ensure(uint64_t(p.nwin) * p.point_bytes));
+  ZKB_CUDA(ctx, s.window_sums.ensure(uint64_t(p.n_sets) * p.point_bytes));
   ZKB_CUDA(ctx, s.result_xyzz.ensure(p.point_bytes));
   ZKB_CUDA(ctx, s.result_affine.ensure(p.point_bytes / 2));
   b->keys_in = (uint32_t*)s.keys_in.p;
@@ -306,7 +306,8 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, boo
 static int msm_prepare(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t n) {
   if (!b || b->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "bases belong to another device");
   if (first > b->n || n > b->n - first) return set_error(ctx, ZKB_EINVAL, "MSM range exceeds the bases");
-  if (b->n >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "MSM larger than 2^31 - 1 points");
+  if (b->n * (b->precomp_c ? b->precomp_nwin : 1) >= (1ull << 31))
+    return set_error(ctx, ZKB_EINVAL, "MSM larger than 2^31 - 1 (expanded) points");
   return ZKB_OK;
 }
 
@@ -330,7 +331,8 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
     ZKB_CUDA(ctx, cudaMemsetAsync(d_out_affine, 0, aff, ctx->stream));
     return ZKB_OK;
   }
-  MsmPlan p = msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
+  MsmPlan p = b->precomp_c ? msm_make_plan(n, b->is_g2, b->precomp_c, ctx->sm_count, b->n)
+                           : msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
   MsmBuffers buf;
   if ((rc = ensure_msm_buffers(ctx, p, &buf))) return rc;
   buf.result_affine = d_out_affine;
@@ -361,9 +363,11 @@ int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_
   uint32_t chunks = ctx->msm_host_chunks > 0 ? uint32_t(ctx->msm_host_chunks) : (n >= (1ull << 20) ? 4 : 1);
   if (chunks > 16) chunks = 16;
   // one window width for the whole MSM so that every chunk fills the same bucket array
-  MsmPlan whole = msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
+  const uint64_t stride = b->precomp_c ? b->n : 0;
+  MsmPlan whole = b->precomp_c ? msm_make_plan(n, b->is_g2, b->precomp_c, ctx->sm_count, stride)
+                               : msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
   const uint64_t per = (n + chunks - 1) / chunks;
-  MsmPlan p = msm_make_plan(per, b->is_g2, whole.c, ctx->sm_count);
+  MsmPlan p = msm_make_plan(per, b->is_g2, whole.c, ctx->sm_count, stride);
   MsmBuffers buf;
   if ((rc = ensure_msm_buffers(ctx, p, &buf, chunks > 1))) return rc;
   buf.result_affine = d_out_affine;
@@ -386,7 +390,7 @@ int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_
   for (uint32_t k = 0; k < chunks; k++) {
     uint64_t off = uint64_t(k) * per;
     uint64_t cnt = n - off < per ? n - off : per;
-    MsmPlan pk = cnt == per ? p : msm_make_plan(cnt, b->is_g2, whole.c, ctx->sm_count);
+    MsmPlan pk = cnt == per ? p : msm_make_plan(cnt, b->is_g2, whole.c, ctx->sm_count, stride);
     pk.sort_temp_bytes = p.sort_temp_bytes;
     ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
     msm_digits_and_sort(pk, buf, (char*)ctx->io_a.p + off * 32, cnt, uint32_t(first + off), ctx->stream);
@@ -513,6 +517,34 @@ int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g
         reinterpret_cast<const uint32_t*>(d_scalars), g1_generator_mont(),
         reinterpret_cast<Affine<Fq>*>(d_out), n);
   ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int bases_precompute_nolock(zkb_ctx* ctx, zkb_bases* b, int c) {
+  if (!b || b->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "bases belong to another device");
+  if (b->precomp_c) return set_error(ctx, ZKB_EINVAL, "bases already carry precomputed multiples");
+  if (b->n == 0) return ZKB_OK;
+  if (c <= 0) c = msm_auto_window(b->n, true);
+  if (c < 2 || c > 24) return set_error(ctx, ZKB_EINVAL, "window width must be in [2, 24]");
+  uint32_t nwin = (255 + c - 1) / c;
+  if (nwin > 32) return set_error(ctx, ZKB_EINVAL, "window width too small for precomputation (more than 32 windows)");
+  if (b->n * nwin >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "expanded base table exceeds 2^31 points");
+  const size_t sz = b->is_g2 ? 128 : 64;
+  void* d_new = nullptr;
+  ZKB_CUDA(ctx, cudaMalloc(&d_new, b->n * nwin * sz));
+  if (b->is_g2) msm_precompute_g2(b->d_pts, d_new, b->n, nwin, c, ctx->stream);
+  else msm_precompute_g1(b->d_pts, d_new, b->n, nwin, c, ctx->stream);
+  ctx->launches++;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(d_new);
+    return cuda_fail(ctx, e, "bases precompute");
+  }
+  cudaFree(b->d_pts);
+  b->d_pts = d_new;
+  b->precomp_c = c;
+  b->precomp_nwin = nwin;
   return ZKB_OK;
 }
 
@@ -662,6 +694,10 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
   if (!std::strcmp(key, "msm_host_chunks")) {
     if (value < 0 || value > 16) return set_error(ctx, ZKB_EINVAL, "msm_host_chunks must be 0..16");
     ctx->msm_host_chunks = value;
+    return ZKB_OK;
+  }
+  if (!std::strcmp(key, "pk_precompute")) {
+    ctx->pk_precompute = value ? 1 : 0;
     return ZKB_OK;
   }
   if (!std::strcmp(key, "msm_profile")) {
@@ -829,6 +865,12 @@ int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_
 }
 
 uint64_t zkb_bases_len(const zkb_bases* b) { return b ? b->n : 0; }
+
+int zkb_bases_precompute(zkb_ctx* ctx, zkb_bases* b, int window_bits) {
+  ZKB_ENTER(ctx);
+  return bases_precompute_nolock(ctx, b, window_bits);
+}
+int zkb_bases_window(const zkb_bases* b) { return b ? b->precomp_c : 0; }
 
 void zkb_bases_free(zkb_bases* b) {
   if (!b) return;

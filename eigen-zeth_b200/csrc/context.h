@@ -65,6 +65,9 @@ struct zkb_bases {
   int is_g2 = 0;
   uint64_t n = 0;
   void* d_pts = nullptr;    // affine Montgomery, 64 / 128 B per point
+  // precomputed window multiples: d_pts holds nwin blocks of n points, block w = 2^{c w} P_i
+  int precomp_c = 0;
+  uint32_t precomp_nwin = 0;
 };
 
 struct zkb_ctx {
@@ -77,6 +80,7 @@ struct zkb_ctx {
   int64_t ntt_full_twiddles = 0;
   int64_t msm_profile = 0;
   int64_t msm_host_chunks = 0;             // 0 = auto
+  int64_t pk_precompute = 1;               // proving-key queries carry precomputed window multiples
   cudaStream_t copy_stream = nullptr;      // H2D of scalar chunks, overlapped with compute
   cudaEvent_t copy_ev[16] = {};
   cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -120,6 +124,7 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
 // host scalars: H2D in chunks on the copy stream, overlapped with the per-chunk MSM front half
 int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
                   uint64_t n, void* d_out_affine);
+int bases_precompute_nolock(zkb_ctx* ctx, zkb_bases* b, int c);
 int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g2, void* d_out);
 int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
                           uint8_t* out);

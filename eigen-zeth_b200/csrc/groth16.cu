@@ -398,6 +398,11 @@ int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t
       tp = tp * tau;
     }
     if ((rc = make_query(ctx, sc, pk->qfirst[4], pk->qcount[4], 0, &pk->h_query))) throw rc;
+    if (ctx->pk_precompute) {
+      zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
+      for (zkb_bases* q : qs)
+        if (q->n && (rc = bases_precompute_nolock(ctx, q, 0))) throw rc;
+    }
     // fixed points: [alpha, beta, delta, ic0, ic1] * G1 and [beta, delta, gamma] * G2
     std::vector<uint64_t> f1(4 * 5), f2(4 * 3);
     canon_into(alpha, f1, 0); canon_into(beta, f1, 1); canon_into(delta, f1, 2);

@@ -10,8 +10,10 @@ namespace zkb {
 struct MsmPlan {
   int c;                    // window width (signed digits in [-2^{c-1}, 2^{c-1}])
   uint32_t nwin;            // ceil(255 / c)
+  uint32_t n_sets;          // bucket sets: nwin, or 1 when the bases carry precomputed window multiples
+  uint64_t val_stride;      // precomputed bases: window w reads point w * val_stride + i (0 otherwise)
   uint32_t half;            // buckets per window = 2^{c-1}
-  uint64_t n_buckets;       // nwin * half (also the sentinel key of zero digits)
+  uint64_t n_buckets;       // n_sets * half (also the sentinel key of zero digits)
   uint64_t m;               // n * nwin (key, value) pairs
   int key_bits;             // radix-sort key width
   uint32_t l1_threads;      // chunks of the level-1 walk
@@ -36,13 +38,19 @@ struct MsmBuffers {
   uint32_t* part2_keys;     // 2 * l2_threads
   void* part2_pts;
   void* group_sums;         // n_groups XYZZ
-  void* window_sums;        // nwin XYZZ
+  void* window_sums;        // n_sets XYZZ
   void* result_xyzz;        // 1 XYZZ (Montgomery)
   void* result_affine;      // 1 affine, canonical little-endian
   cudaEvent_t* ev;          // optional 6 profiling events: start, digits, sort, L1, L2+finish, tail
 };
 
-MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count);
+// precomp_stride != 0: the bases hold 2^{c w} P_i at index w * precomp_stride + i for every window w
+// (c_override is then the width they were built for) and all windows share one bucket set.
+MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint64_t precomp_stride = 0);
+int msm_auto_window(uint64_t n, bool precomputed);
+// out[w * n + i] = 2^{c w} * in[i], w < nwin (affine Montgomery in and out; in may alias out[0..n))
+void msm_precompute_g1(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);
+void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);
 // scalars[0..n) -> sorted (key, value) stream; values carry idx_base + i.  Non-canonical scalars
 // (>= r) raise bit 0 of *d_flag.
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,

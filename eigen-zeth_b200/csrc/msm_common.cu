@@ -12,7 +12,7 @@ namespace zkb {
 __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t c,
                                   uint32_t nwin, uint32_t* __restrict__ keys,
                                   uint32_t* __restrict__ vals, uint32_t idx_base,
-                                  uint32_t* __restrict__ flag) {
+                                  uint32_t* __restrict__ flag, uint32_t val_stride) {
   uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
@@ -33,7 +33,8 @@ __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t
   }
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (1u << c) - 1;
-  const uint32_t sentinel = nwin * half;
+  const bool one_set = val_stride != 0;       // precomputed window multiples: a single bucket set
+  const uint32_t sentinel = (one_set ? 1u : nwin) * half;
   uint32_t carry = 0;
   for (uint32_t w = 0; w < nwin; w++) {
     uint32_t bit = w * c;
@@ -47,9 +48,9 @@ __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t
     uint32_t neg = d > half;
     uint32_t mag = neg ? (1u << c) - d : d;
     carry = neg;
-    uint32_t key = mag ? w * half + (mag - 1) : sentinel;
+    uint32_t key = mag ? (one_set ? 0u : w * half) + (mag - 1) : sentinel;
     keys[uint64_t(w) * n + i] = key;
-    vals[uint64_t(w) * n + i] = (idx_base + uint32_t(i)) | (neg << 31);
+    vals[uint64_t(w) * n + i] = (w * val_stride + idx_base + uint32_t(i)) | (neg << 31);
   }
 }
 
@@ -72,19 +73,27 @@ size_t msm_sort_temp_bytes(uint64_t m, int end_bit) {
   return bytes;
 }
 
-MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count) {
-  MsmPlan p{};
+int msm_auto_window(uint64_t n, bool precomputed) {
   int log_n = 0;
   while ((1ull << log_n) < n) log_n++;
-  int c = c_override > 0 ? c_override : log_n - 6;
-  if (c_override <= 0) {
-    if (c < 4) c = 4;
-    if (c > 16) c = 16;
-  }
+  // classic: W bucket sets, keep buckets << points.  precomputed: ONE bucket set shared by all
+  // windows, so the width can grow until the bucket reduction (2 adds per bucket) shows.
+  int c = precomputed ? log_n - 4 : log_n - 6;
+  int lo = precomputed ? 8 : 4, hi = precomputed ? 20 : 16;
+  if (c < lo) c = lo;
+  if (c > hi) c = hi;
+  return c;
+}
+
+MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint64_t precomp_stride) {
+  MsmPlan p{};
+  int c = c_override > 0 ? c_override : msm_auto_window(n, precomp_stride != 0);
   p.c = c;
   p.nwin = (255 + c - 1) / c;
   p.half = 1u << (c - 1);
-  p.n_buckets = uint64_t(p.nwin) * p.half;
+  p.n_sets = precomp_stride ? 1 : p.nwin;
+  p.val_stride = precomp_stride;
+  p.n_buckets = uint64_t(p.n_sets) * p.half;
   p.m = n * p.nwin;
   p.key_bits = 1;
   while ((1ull << p.key_bits) <= p.n_buckets) p.key_bits++;   // sentinel == n_buckets must fit
@@ -99,7 +108,7 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count) {
   p.l2_threads = (2 * p.l1_threads + p.l2_len - 1) / p.l2_len;
   p.gsize = p.half < 32 ? p.half : 32;
   p.groups_per_win = p.half / p.gsize;
-  p.n_groups = p.groups_per_win * p.nwin;
+  p.n_groups = p.groups_per_win * p.n_sets;
   p.point_bytes = is_g2 ? 256 : 128;
   p.sort_temp_bytes = msm_sort_temp_bytes(p.m, p.key_bits);
   return p;
@@ -112,7 +121,8 @@ void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_sc
   uint32_t blocks = uint32_t((n + 255) / 256);
   if (blocks)
     msm_digits_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, p.c,
-                                             p.nwin, b.keys_in, b.vals_in, idx_base, b.flag);
+                                             p.nwin, b.keys_in, b.vals_in, idx_base, b.flag,
+                                             uint32_t(p.val_stride));
   if (b.ev) cudaEventRecord(b.ev[1], s);
   size_t temp = p.sort_temp_bytes;
   cub::DeviceRadixSort::SortPairs(b.sort_temp, temp, (const uint32_t*)b.keys_in, b.keys_out,

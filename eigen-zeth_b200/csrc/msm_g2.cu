@@ -14,4 +14,7 @@ void msm_bases_to_mont_g2(void* d_pts, uint64_t n, cudaStream_t s) { msm_bases_t
 void msm_sum_affine_g2(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s) {
   msm_sum_affine_t<Fq2>(d_pts, n, d_out, s);
 }
+void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s) {
+  msm_precompute_t<Fq2>(d_in, d_out, n, nwin, c, s);
+}
 }  // namespace zkb

@@ -294,13 +294,59 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
   msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
       reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
       reinterpret_cast<P*>(b.group_sums));
-  msm_window_sum_kernel<F><<<p.nwin, 128, 128 * sizeof(P), s>>>(
+  msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(
       reinterpret_cast<const P*>(b.group_sums), p.groups_per_win,
       reinterpret_cast<P*>(b.window_sums));
-  msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.nwin, p.c,
+  msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.n_sets, p.c,
                                         reinterpret_cast<P*>(b.result_xyzz),
                                         reinterpret_cast<Affine<F>*>(b.result_affine));
   if (b.ev) cudaEventRecord(b.ev[5], s);
+}
+
+// ---------------------------------------------------------------- precomputed window multiples
+// out[w * n + i] = 2^{c w} P_i.  One thread per base: a chain of c doublings per window in XYZZ,
+// all windows brought back to affine with ONE inversion (Montgomery's trick over the chain).
+constexpr int kMaxPrecompWindows = 32;
+
+template <class F>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<F>* __restrict__ in,
+                                                             Affine<F>* __restrict__ out, uint64_t n,
+                                                             uint32_t nwin, uint32_t c) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p0 = Affine<F>::load(in + i);
+  p0.store(out + i);
+  if (p0.is_inf()) {
+    for (uint32_t w = 1; w < nwin; w++) Affine<F>{F::zero(), F::zero()}.store(out + uint64_t(w) * n + i);
+    return;
+  }
+  // a point of odd prime order never doubles to infinity, so every zzz below is invertible
+  XYZZ<F> pts[kMaxPrecompWindows];
+  F prefix[kMaxPrecompWindows];
+  XYZZ<F> acc = XYZZ<F>::from_affine(p0);
+  F run = F::one();
+  for (uint32_t w = 1; w < nwin; w++) {
+    for (uint32_t k = 0; k < c; k++) acc = acc.dbl();
+    pts[w] = acc;
+    prefix[w] = run;              // product of zzz_1 .. zzz_{w-1}
+    run = run * acc.zzz;
+  }
+  F inv = run.inverse();
+  for (uint32_t w = nwin - 1; w >= 1; w--) {
+    F zi = inv * prefix[w];       // 1 / zzz_w
+    inv = inv * pts[w].zzz;
+    F zi2 = (zi * pts[w].zz).sqr();   // 1 / zz_w
+    Affine<F> a{pts[w].x * zi2, pts[w].y * zi};
+    a.store(out + uint64_t(w) * n + i);
+  }
+}
+
+template <class F>
+void msm_precompute_t(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s) {
+  uint32_t blocks = uint32_t((n + 127) / 128);
+  if (blocks)
+    msm_precompute_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<const Affine<F>*>(d_in),
+                                                    reinterpret_cast<Affine<F>*>(d_out), n, nwin, c);
 }
 
 template <class F>

@@ -19,6 +19,7 @@ EXPORTS = [
     "zkb_version", "zkb_ctx_create", "zkb_ctx_destroy", "zkb_last_error", "zkb_ctx_stream", "zkb_ctx_sync",
     "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
+    "zkb_bases_precompute", "zkb_bases_window",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
@@ -75,6 +76,8 @@ def load_library() -> C.CDLL:
     lib.zkb_bases_download.argtypes = [vp, vp, u64, u64, vp]
     lib.zkb_bases_len.argtypes = [vp]
     lib.zkb_bases_len.restype = u64
+    lib.zkb_bases_precompute.argtypes = [vp, vp, i32]
+    lib.zkb_bases_window.argtypes = [vp]
     lib.zkb_bases_free.argtypes = [vp]
     lib.zkb_bases_free.restype = None
     if hasattr(lib, "zkb_pk_synthetic"):
@@ -113,6 +116,15 @@ class Bases:
 
     def __len__(self):
         return int(self.ctx.lib.zkb_bases_len(self.handle))
+
+    def precompute(self, window_bits: int = 0) -> int:
+        """expand to window multiples in HBM (zkb_bases_precompute); returns the window width."""
+        self.ctx._check(self.ctx.lib.zkb_bases_precompute(self.ctx.h, self.handle, window_bits))
+        return int(self.ctx.lib.zkb_bases_window(self.handle))
+
+    @property
+    def window(self) -> int:
+        return int(self.ctx.lib.zkb_bases_window(self.handle))
 
     def download(self, first=0, count=None) -> bytes:
         count = len(self) - first if count is None else count

@@ -46,7 +46,8 @@ void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(const zkb_ctx* ctx);
 void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
-/* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1) */
+/* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1),
+ * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
 
@@ -68,6 +69,13 @@ int zkb_bases_synthetic_g2(zkb_ctx* ctx, uint64_t n, uint64_t seed, zkb_bases** 
 int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
                        uint8_t* out);
 uint64_t zkb_bases_len(const zkb_bases* b);
+/* Expand the bases in HBM to their window multiples 2^{c w} P_i (ceil(255/c) copies: the B200's
+ * 180 GB is the resource being spent).  Every window then feeds ONE shared bucket set: no Horner
+ * pass, a bucket reduction of a single window, and a wider window (fewer additions) for the same
+ * bucket count.  window_bits = 0 picks the width from the number of points.  Proving-key queries
+ * are fixed, so this is done once per key.  MSM results are unchanged (bit-exact). */
+int zkb_bases_precompute(zkb_ctx* ctx, zkb_bases* b, int window_bits);
+int zkb_bases_window(const zkb_bases* b);          /* 0 = not precomputed */
 void zkb_bases_free(zkb_bases* b);
 /* sum_i scalars[i] * bases[first + i], i < n; host scalars; result canonical affine (64 / 128 B) */
 int zkb_msm_g1(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,

@@ -117,3 +117,48 @@ def test_synthetic_g2_closed_form(ctx):
     sc = [srng.fr() for _ in range(n)]
     want = o.g2_mul(o.G2_GEN, sum(s * k for s, k in zip(sc, ks)) % o.R)
     assert o.g2_from_bytes(ctx.msm(bases, fr_bytes(sc))) == want
+
+
+@pytest.mark.parametrize("n,window", [(1, 0), (37, 8), (300, 0), (300, 13), (300, 20)])
+def test_precomputed_window_multiples_g1(ctx, n, window):
+    """bases expanded to 2^{cw} P_i in HBM (zkb_bases_precompute): one shared bucket set, no Horner
+    pass; results must not change."""
+    rng = o.Xoshiro256ss(4000 + n + window)
+    pts = _g1_points(rng, n)
+    if n > 10:
+        pts[3] = None
+        pts[5] = pts[6]
+        pts[7] = o.g1_neg(pts[8])
+    bases = ctx.upload_bases(g1_bytes(pts))
+    c = bases.precompute(window)
+    assert c == (window or bases.window) and c >= 8
+    assert g1_list(bases.download()) == pts                  # block 0 is still the original points
+    for sc in (rand_fr(rng, n), [o.R - 1] * n, [1] * n, [0] * n, [(i * 5) & 1 for i in range(n)]):
+        assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g1(pts, sc)
+    if n > 10:   # sub-range of precomputed bases
+        sc = rand_fr(rng, 50)
+        assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc), first=100)) == o.msm_g1(pts[100:150], sc)
+
+
+def test_precomputed_g2_and_large_closed_form(ctx):
+    rng = o.Xoshiro256ss(4242)
+    pts = _g2_points(rng, 70)
+    pts[1] = None
+    sc = rand_fr(rng, 70)
+    bases = ctx.upload_bases(g2_bytes(pts), g2=True)
+    bases.precompute(0)
+    assert o.g2_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g2(pts, sc)
+    n, seed = 1 << 17, 0x5EED0009
+    big = ctx.synthetic_bases(n, seed)
+    krng = o.Xoshiro256ss(seed)
+    ks = [krng.fr() for _ in range(n)]
+    sc = rand_fr(rng, n)
+    want = o.g1_mul(o.G1_GEN, sum(s * k for s, k in zip(sc, ks)) % o.R)
+    assert o.g1_from_bytes(ctx.msm(big, fr_bytes(sc))) == want
+    big.precompute(0)
+    assert o.g1_from_bytes(ctx.msm(big, fr_bytes(sc))) == want
+    ctx.set("msm_host_chunks", 3)
+    try:
+        assert o.g1_from_bytes(ctx.msm(big, fr_bytes(sc))) == want
+    finally:
+        ctx.set("msm_host_chunks", 0)
