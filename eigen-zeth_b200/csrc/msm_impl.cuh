@@ -28,9 +28,14 @@ namespace zkb {
 
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 
+// resident CTAs (of 128 threads) per SM for the level-1 walk: 4 x 128 threads at <= 128 registers
+// for G1; the Fq2 accumulator needs the full 255 registers, so 2 x 128 for G2
+template <class F> struct L1Cfg { static constexpr int kMinBlocks = 4; };
+template <> struct L1Cfg<Fq2> { static constexpr int kMinBlocks = 2; };
+
 // ---------------------------------------------------------------- 3. accumulate, level 1
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_l1_kernel(
+__global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_kernel(
     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
     const uint64_t* __restrict__ m_valid_ptr, const Affine<F>* __restrict__ bases,
     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
@@ -174,16 +179,20 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(
 }
 
 // ---------------------------------------------------------------- 7. window sum
+// CTA (set, slice) sums its slice of the `count` points of a set (serial per thread, then a shared
+// memory tree).  Launched twice: group sums -> `slices` partials per set -> one point per set.
 template <class F>
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __restrict__ group_sums,
-                                                             uint32_t groups_per_win,
-                                                             XYZZ<F>* __restrict__ window_sums) {
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __restrict__ in,
+                                                             uint32_t count, uint32_t slices,
+                                                             XYZZ<F>* __restrict__ out) {
   extern __shared__ uint4 sm_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sm_raw);
-  const uint32_t w = blockIdx.x, t = threadIdx.x;
+  const uint32_t set = blockIdx.x / slices, slice = blockIdx.x - set * slices, t = threadIdx.x;
+  const uint32_t len = (count + slices - 1) / slices;
+  const uint32_t lo = slice * len, hi = lo + len < count ? lo + len : count;
   XYZZ<F> acc = XYZZ<F>::infinity();
-  for (uint32_t g = t; g < groups_per_win; g += blockDim.x)
-    acc.add(XYZZ<F>::load(group_sums + uint64_t(w) * groups_per_win + g));
+  for (uint32_t g = lo + t; g < hi; g += blockDim.x)
+    acc.add(XYZZ<F>::load(in + uint64_t(set) * count + g));
   acc.store(sm + t);
   __syncthreads();
   for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __re
     }
     __syncthreads();
   }
-  if (t == 0) XYZZ<F>::load(sm).store(window_sums + w);
+  if (t == 0) XYZZ<F>::load(sm).store(out + blockIdx.x);
 }
 
 // ---------------------------------------------------------------- 8. Horner + output
@@ -294,9 +303,15 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
   msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
       reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
       reinterpret_cast<P*>(b.group_sums));
-  msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(
-      reinterpret_cast<const P*>(b.group_sums), p.groups_per_win,
-      reinterpret_cast<P*>(b.window_sums));
+  // two-stage sum of the group results of every set
+  const uint32_t slices = p.groups_per_win >= 4096 ? 64 : (p.groups_per_win >= 256 ? 8 : 1);
+  P* stage = reinterpret_cast<P*>(b.group_sums) + p.n_groups;     // scratch behind the group sums
+  msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(
+      reinterpret_cast<const P*>(b.group_sums), p.groups_per_win, slices,
+      slices > 1 ? stage : reinterpret_cast<P*>(b.window_sums));
+  if (slices > 1)
+    msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(
+        stage, slices, 1, reinterpret_cast<P*>(b.window_sums));
   msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.n_sets, p.c,
                                         reinterpret_cast<P*>(b.result_xyzz),
                                         reinterpret_cast<Affine<F>*>(b.result_affine));
