@@ -182,8 +182,9 @@ int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out) {
 }
 
 int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
-            const void* pre_scale, const void* post_scale, int /*fold_ninv*/, int mont_in,
-            int mont_out) {
+            const void* pre_scale, const void* post_scale, int skip_ninv, int mont_in,
+            int mont_out, uint64_t batch) {
+  if (batch == 0) return ZKB_OK;
   if (log_n < 1 || log_n > 28) return set_error(ctx, ZKB_EINVAL, "log_n must be in [1, 28]");
   int rc = ensure_stage_tables(ctx);
   if (rc) return rc;
@@ -191,8 +192,12 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
   if ((rc = get_domain(ctx, log_n, inverse, &d))) return rc;
   const size_t P = d->ks.size();
   const uint64_t n = 1ull << log_n;
-  if (P > 1 && ctx->ntt_full_twiddles && (rc = ensure_full_tables(ctx, d, inverse))) return rc;
-  if (inverse && P == 1 && !post_scale) {
+  const uint64_t total = n * batch;
+  if ((total >> 11) * 8 >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "batch too large");
+  const bool use_full = P > 1 && ctx->ntt_full_twiddles && !skip_ninv;
+  if (use_full && (rc = ensure_full_tables(ctx, d, inverse))) return rc;
+  if (inverse && P == 1 && !post_scale && !skip_ninv) {
+    if (batch != 1) return set_error(ctx, ZKB_EINVAL, "batched single-pass inverse needs an explicit scale table");
     CosetTables* t;
     if ((rc = coset_tables(ctx, log_n, &t))) return rc;
     post_scale = t->ninv.p;
@@ -209,7 +214,7 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
   a.tw_lo_mask = (1ull << d->lo_bits) - 1;
   void* work = d_out;
   if (P > 1) {
-    ZKB_CUDA(ctx, ctx->ntt_tmp.ensure(n * 32));
+    ZKB_CUDA(ctx, ctx->ntt_tmp.ensure(total * 32));
     work = ctx->ntt_tmp.p;
   }
   uint64_t M = n;
@@ -222,14 +227,14 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     a.M = M;
     a.S = uint32_t(M >> k);
     a.tw_shift = log_n - log_m;
-    a.tw_hi = (p == 0 && inverse) ? d->tw_hi_ninv.p : d->tw_hi.p;
-    a.tw_full = (ctx->ntt_full_twiddles && d->full_ready) ? d->full[p].p : nullptr;
+    a.tw_hi = (p == 0 && inverse && !skip_ninv) ? d->tw_hi_ninv.p : d->tw_hi.p;
+    a.tw_full = (use_full && d->full_ready) ? d->full[p].p : nullptr;
     a.pre_scale = p == 0 ? pre_scale : nullptr;
     a.post_scale = nullptr;
     a.mont_in = p == 0 ? mont_in : 1;
     a.mont_out = 1;
     uint32_t CT = 8u << (8 - k);
-    uint32_t tiles = uint32_t(n / M) * ((a.S + CT - 1) / CT);
+    uint32_t tiles = uint32_t(total / M) * ((a.S + CT - 1) / CT);
     ntt_launch_pass(a, false, tiles, ctx->stream);
     ctx->launches++;
     M >>= k;
@@ -252,7 +257,9 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     uint32_t CT = 8u << (8 - k);
     uint32_t k0_range = 1u << a.first_digit_bits;
     uint32_t tiles = ((k0_range + CT - 1) / CT) << (a.row_bits - a.first_digit_bits);
-    ntt_launch_pass(a, true, tiles, ctx->stream);
+    a.batch_log = log_n;
+    a.tiles_per_batch = batch > 1 ? tiles : 0;
+    ntt_launch_pass(a, true, uint32_t(tiles * batch), ctx->stream);
     ctx->launches++;
   }
   ZKB_CUDA(ctx, cudaGetLastError());
@@ -346,6 +353,54 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
   } else {
     msm_accumulate_g1(p, buf, b->d_pts, buf.buckets, ctx->stream);
     msm_tail_g1(p, buf, ctx->stream);
+  }
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+// k MSMs over the SAME scalars (the A / B1 / B2 / L MSMs of a Groth16 proof all use the witness):
+// digits and sort run once, accumulate + tail once per base set.  All base sets must have the same
+// length and window layout.  ev_opt[j] (optional) is recorded after MSM j.
+int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* d_scalars, uint64_t first,
+                   uint64_t n, void* const* d_outs, cudaEvent_t* ev_opt) {
+  if (k <= 0) return ZKB_OK;
+  for (int j = 0; j < k; j++) {
+    int rc = msm_prepare(ctx, bs[j], first, n);
+    if (rc) return rc;
+    if (bs[j]->n != bs[0]->n || bs[j]->precomp_c != bs[0]->precomp_c)
+      return set_error(ctx, ZKB_EINVAL, "shared-scalar MSMs need base sets of one shape");
+  }
+  if (n == 0) {
+    for (int j = 0; j < k; j++) {
+      ZKB_CUDA(ctx, cudaMemsetAsync(d_outs[j], 0, bs[j]->is_g2 ? 128 : 64, ctx->stream));
+      if (ev_opt) cudaEventRecord(ev_opt[j], ctx->stream);
+    }
+    return ZKB_OK;
+  }
+  const zkb_bases* b0 = bs[0];
+  int any_g2 = 0;
+  for (int j = 0; j < k; j++) any_g2 |= bs[j]->is_g2;
+  // buffers sized for the widest point type; the chunk walk uses each group's own thread count
+  MsmPlan p1 = b0->precomp_c ? msm_make_plan(n, 0, b0->precomp_c, ctx->sm_count, b0->n)
+                             : msm_make_plan(n, 0, int(ctx->msm_window), ctx->sm_count);
+  MsmPlan p2 = msm_make_plan(n, 1, p1.c, ctx->sm_count, p1.val_stride);
+  MsmBuffers buf;
+  int rc;
+  if (any_g2 && (rc = ensure_msm_buffers(ctx, p2, &buf))) return rc;
+  if ((rc = ensure_msm_buffers(ctx, p1, &buf))) return rc;
+  msm_digits_and_sort(p1, buf, d_scalars, n, uint32_t(first), ctx->stream);
+  ctx->launches += 2;
+  for (int j = 0; j < k; j++) {
+    buf.result_affine = d_outs[j];
+    if (bs[j]->is_g2) {
+      msm_accumulate_g2(p2, buf, bs[j]->d_pts, buf.buckets, ctx->stream);
+      msm_tail_g2(p2, buf, ctx->stream);
+    } else {
+      msm_accumulate_g1(p1, buf, bs[j]->d_pts, buf.buckets, ctx->stream);
+      msm_tail_g1(p1, buf, ctx->stream);
+    }
+    ctx->launches += 7;
+    if (ev_opt) cudaEventRecord(ev_opt[j], ctx->stream);
   }
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
@@ -730,6 +785,59 @@ int zkb_fr_ntt_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, 
     if (inverse) post = t->inv.p; else pre = t->fwd.p;
   }
   return ntt_run(ctx, d_in, d_out, log_n, inverse, pre, post, 0, montgomery, montgomery);
+}
+
+// ---- building blocks of the distributed (four-step) NTT; all asynchronous on device buffers
+int zkb_fr_ntt_batch_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_size, uint64_t batch,
+                         int inverse, int skip_ninv, const void* d_pre_table, const void* d_post_table) {
+  ZKB_ENTER(ctx);
+  if (!d_in || !d_out) return set_error(ctx, ZKB_EINVAL, "null buffer");
+  return ntt_run(ctx, d_in, d_out, log_size, inverse, d_pre_table, d_post_table, skip_ninv, 1, 1, batch);
+}
+int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, uint32_t b, uint32_t c) {
+  ZKB_ENTER(ctx);
+  if (!d_in || !d_out || d_in == d_out) return set_error(ctx, ZKB_EINVAL, "permute needs distinct buffers");
+  fr_permute_launch(d_in, d_out, a, b, c, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const uint8_t scale[32], uint64_t rows,
+                     uint64_t cols, uint64_t row0, uint64_t mul, int mode) {
+  ZKB_ENTER(ctx);
+  HFr b, c;
+  if (!d_out || !base || !scale || !HFr::from_bytes(base, &b) || !HFr::from_bytes(scale, &c) || mode < 0 || mode > 1)
+    return set_error(ctx, ZKB_EINVAL, "bad table argument");
+  uint32_t bw[8], cw[8];
+  hfr_to_words(b, bw);
+  hfr_to_words(c, cw);
+  fr_table_launch(d_out, bw, cw, rows, cols, row0, mul, mode, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+int zkb_fr_mul_sub_dev(zkb_ctx* ctx, void* d_a, const void* d_b, const void* d_c, uint64_t n) {
+  ZKB_ENTER(ctx);
+  if (!d_a || !d_b || !d_c) return set_error(ctx, ZKB_EINVAL, "null buffer");
+  fr_mul_sub_launch(d_a, d_b, d_c, n, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+int zkb_fr_convert_dev(zkb_ctx* ctx, void* d_data, uint64_t n, int to_montgomery) {
+  ZKB_ENTER(ctx);
+  if (!d_data) return set_error(ctx, ZKB_EINVAL, "null buffer");
+  fr_convert_launch(d_data, n, to_montgomery, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+void zkb_fr_root_of_unity(uint32_t log_n, int inverse, uint8_t out[32]) {
+  uint32_t w[8];
+  host_fr_root(log_n, inverse, w);
+  HFr a;
+  std::memcpy(a.l, w, 32);
+  a.to_bytes(out);
 }
 
 static bool all_canonical_fr(const uint8_t* data, uint64_t n) {

@@ -115,12 +115,16 @@ int cuda_fail(zkb_ctx* ctx, cudaError_t e, const char* what);
   } while (0)
 
 // internal device-level entry points (used by the C ABI wrappers and by the Groth16 pipeline)
+// `batch` contiguous transforms of 2^log_n elements each (tables, if given, cover the whole batch).
+// skip_ninv: an inverse transform without the 1/n factor (the caller folds it elsewhere).
 int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
-            const void* pre_scale, const void* post_scale, int fold_ninv, int mont_in,
-            int mont_out);
+            const void* pre_scale, const void* post_scale, int skip_ninv, int mont_in,
+            int mont_out, uint64_t batch = 1);
 int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out);
 int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
              void* d_out_affine);
+int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* d_scalars, uint64_t first,
+                   uint64_t n, void* const* d_outs, cudaEvent_t* ev_opt);
 // host scalars: H2D in chunks on the copy stream, overlapped with the per-chunk MSM front half
 int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
                   uint64_t n, void* d_out_affine);

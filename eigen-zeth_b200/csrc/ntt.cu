@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
   uint32_t r_base = 0;    // column mode
   uint32_t c_base = 0;    // final mode: first K_0 of this tile
   uint32_t mid = 0;       // final mode: the remaining (lower) row digits
+  uint64_t batch_off = 0; // final mode: first element of this tile's transform within a batch
   uint32_t ncols;         // valid columns in this tile
   if (!FINAL) {
     uint32_t tiles_per_blk = (p.S + CT - 1) >> ct_bits;
@@ -143,6 +144,12 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
     base = uint64_t(blk) * p.M + r_base;
     ncols = min(uint32_t(CT), p.S - r_base);
   } else {
+    // a contiguous batch of transforms: tile -> (transform, tile within it)
+    if (p.tiles_per_batch) {
+      uint32_t bidx = tile / p.tiles_per_batch;
+      tile -= bidx * p.tiles_per_batch;
+      batch_off = uint64_t(bidx) << p.batch_log;
+    }
     // row number rho = K0 * 2^{mid_bits} + mid ; tiles enumerate (mid, K0 / CT)
     uint32_t k0_range = 1u << p.first_digit_bits;
     uint32_t tiles_per_mid = (k0_range + CT - 1) >> ct_bits;
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
     if (c < ncols) {
       uint64_t idx;
       if (!FINAL) idx = base + uint64_t(t) * p.S + c;
-      else idx = ((uint64_t(c_base + c) << mid_bits) + mid) * (1u << k) + t;
+      else idx = batch_off + ((uint64_t(c_base + c) << mid_bits) + mid) * (1u << k) + t;
       x = Fr::load_nc(in + idx * 32);
       if (!p.mont_in) {
         if (!fr_is_canonical(x)) atomicOr(p.flag, 1u);
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
       }
     } else {
       uint32_t rho = ((c_base + c) << mid_bits) + mid;
-      idx = uint64_t(row_reverse(rho, p)) + (uint64_t(K) << p.row_bits);
+      idx = batch_off + uint64_t(row_reverse(rho, p)) + (uint64_t(K) << p.row_bits);
       if (p.post_scale)
         y = y * Fr::load_nc(reinterpret_cast<const char*>(p.post_scale) + idx * 32);
     }
@@ -314,6 +321,40 @@ __global__ void fr_convert_kernel(Fr* data, uint64_t n, int to_mont) {
   x.store(data + i);
 }
 
+// [A][B][C] -> [B][A][C] on 32-byte elements; one thread per 16-byte half for coalescing
+__global__ void fr_permute_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t A,
+                                  uint32_t B, uint32_t C) {
+  uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;     // output half-element index
+  uint64_t total = uint64_t(A) * B * C * 2;
+  if (q >= total) return;
+  uint64_t e = q >> 1;
+  uint32_t c = uint32_t(e % C);
+  uint64_t r = e / C;
+  uint32_t a = uint32_t(r % A), b = uint32_t(r / A);
+  out[q] = in[(((uint64_t(a) * B + b) * C + c) << 1) | (q & 1)];
+}
+
+__global__ void fr_table_kernel(Fr* out, Fr base, Fr c, uint64_t rows, uint64_t cols, uint64_t row0,
+                                uint64_t mul, int mode) {
+  uint64_t pos = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (pos >= rows * cols) return;
+  uint64_t hi = pos / cols, lo = pos - hi * cols;
+  uint64_t e = mode == 0 ? (row0 + hi) * lo : (row0 + hi) + lo * mul;
+  Fr r = c, b = base;
+  while (e) {
+    if (e & 1) r = r * b;
+    b = b.sqr();
+    e >>= 1;
+  }
+  r.store(out + pos);
+}
+
+__global__ void fr_mul_sub_kernel(Fr* a, const Fr* b, const Fr* c, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  (Fr::load(a + i) * Fr::load(b + i) - Fr::load(c + i)).store(a + i);
+}
+
 // ---------------------------------------------------------------- host side
 void ntt_launch_pass(const NttPassArgs& a, bool final, uint32_t tiles, cudaStream_t s) {
   static bool configured = false;
@@ -345,6 +386,28 @@ void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t 
                                                 reinterpret_cast<const Fr*>(lo),
                                                 reinterpret_cast<const Fr*>(hi), lo_bits, tw_shift,
                                                 s_bits, M);
+}
+
+void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32_t C, cudaStream_t s) {
+  uint64_t total = uint64_t(A) * B * C * 2;
+  uint32_t blocks = uint32_t((total + 255) / 256);
+  if (blocks)
+    fr_permute_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), A, B, C);
+}
+
+void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t rows, uint64_t cols,
+                     uint64_t row0, uint64_t mul, int mode, cudaStream_t s) {
+  Fr b, cc;
+  for (int i = 0; i < 8; i++) { b.v[i] = base[i]; cc.v[i] = c[i]; }
+  uint32_t blocks = uint32_t((rows * cols + 255) / 256);
+  if (blocks) fr_table_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(out), b, cc, rows, cols, row0, mul, mode);
+}
+
+void fr_mul_sub_launch(void* a, const void* b, const void* c, uint64_t n, cudaStream_t s) {
+  uint32_t blocks = uint32_t((n + 255) / 256);
+  if (blocks)
+    fr_mul_sub_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(a), reinterpret_cast<const Fr*>(b),
+                                             reinterpret_cast<const Fr*>(c), n);
 }
 
 void fr_convert_launch(void* data, uint64_t n, int to_mont, cudaStream_t s) {

@@ -25,6 +25,8 @@ struct NttPassArgs {
   uint32_t first_digit_bits;  // final mode: width of K_0 (0 when P == 1)
   uint32_t n_row_digits;
   uint32_t row_digit_bits[4];
+  uint32_t batch_log;      // each transform covers 2^batch_log elements; tiles beyond one transform's
+  uint32_t tiles_per_batch;//   count belong to the next transform of a contiguous batch (final mode)
   uint32_t* flag;          // bit 0 raised when a canonical-form input (mont_in == 0) is >= r
   int mont_in;             // 0: input is canonical integers, convert while loading
   int mont_out;            // 0: convert the result back to canonical integers while storing
@@ -36,5 +38,14 @@ void fr_powers_launch(void* out, const uint32_t base[8], const uint32_t c[8], ui
 void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t lo_bits,
                             uint32_t tw_shift, uint32_t s_bits, uint64_t M, cudaStream_t s);
 void fr_convert_launch(void* data, uint64_t n, int to_mont, cudaStream_t s);
+// out[(b*A + a)*C + c] = in[(a*B + b)*C + c]  : [A][B][C] -> [B][A][C]   (32-byte elements)
+void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32_t C, cudaStream_t s);
+// index-mapped power tables for the distributed (four-step) NTT, pos = hi * cols + lo:
+//   mode 0: out[pos] = c * base^{(row0 + hi) * lo}            (inter-step twiddle  w^{i2 * k1})
+//   mode 1: out[pos] = c * base^{(row0 + hi) + lo * mul}      (coset powers at global index k1 + N1 k2)
+void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t rows, uint64_t cols,
+                     uint64_t row0, uint64_t mul, int mode, cudaStream_t s);
+// a[i] = a[i] * b[i] - c[i]
+void fr_mul_sub_launch(void* a, const void* b, const void* c, uint64_t n, cudaStream_t s);
 
 }  // namespace zkb

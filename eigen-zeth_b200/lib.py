@@ -17,7 +17,8 @@ VK_BYTES, PROOF_BYTES, INTERMEDIATE_BYTES = 576, 256, 384
 
 EXPORTS = [
     "zkb_version", "zkb_ctx_create", "zkb_ctx_destroy", "zkb_last_error", "zkb_ctx_stream", "zkb_ctx_sync",
-    "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
+    "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_fr_ntt_batch_dev", "zkb_fr_permute_dev", "zkb_fr_table_dev",
+    "zkb_fr_mul_sub_dev", "zkb_fr_convert_dev", "zkb_fr_root_of_unity", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_bases_precompute", "zkb_bases_window",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
@@ -67,6 +68,13 @@ def load_library() -> C.CDLL:
     lib.zkb_ctx_set.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.zkb_fr_ntt.argtypes = [vp, vp, u32, i32, i32]
     lib.zkb_fr_ntt_dev.argtypes = [vp, vp, vp, u32, i32, i32, i32]
+    lib.zkb_fr_ntt_batch_dev.argtypes = [vp, vp, vp, u32, u64, i32, i32, vp, vp]
+    lib.zkb_fr_permute_dev.argtypes = [vp, vp, vp, u32, u32, u32]
+    lib.zkb_fr_table_dev.argtypes = [vp, vp, u8p, u8p, u64, u64, u64, u64, i32]
+    lib.zkb_fr_mul_sub_dev.argtypes = [vp, vp, vp, vp, u64]
+    lib.zkb_fr_convert_dev.argtypes = [vp, vp, u64, i32]
+    lib.zkb_fr_root_of_unity.argtypes = [u32, i32, vp]
+    lib.zkb_fr_root_of_unity.restype = None
     for g in ("g1", "g2"):
         getattr(lib, "zkb_bases_upload_" + g).argtypes = [vp, u8p, u64, C.POINTER(vp)]
         getattr(lib, "zkb_bases_synthetic_" + g).argtypes = [vp, u64, u64, C.POINTER(vp)]
@@ -225,6 +233,22 @@ class Context:
     def fr_ntt_dev(self, d_in: int, d_out: int, log_n: int, inverse=False, coset=False, montgomery=False):
         self._check(self.lib.zkb_fr_ntt_dev(self.h, d_in, d_out, log_n, int(inverse), int(coset), int(montgomery)))
 
+    def fr_ntt_batch_dev(self, d_in, d_out, log_size, batch, inverse=False, skip_ninv=False, pre=0, post=0):
+        self._check(self.lib.zkb_fr_ntt_batch_dev(self.h, d_in, d_out, log_size, batch, int(inverse), int(skip_ninv),
+                                                  pre or None, post or None))
+
+    def fr_permute_dev(self, d_in, d_out, a, b, c):
+        self._check(self.lib.zkb_fr_permute_dev(self.h, d_in, d_out, a, b, c))
+
+    def fr_table_dev(self, d_out, base: bytes, scale: bytes, rows, cols, row0, mul, mode):
+        self._check(self.lib.zkb_fr_table_dev(self.h, d_out, base, scale, rows, cols, row0, mul, mode))
+
+    def fr_mul_sub_dev(self, d_a, d_b, d_c, n):
+        self._check(self.lib.zkb_fr_mul_sub_dev(self.h, d_a, d_b, d_c, n))
+
+    def fr_convert_dev(self, d_data, n, to_montgomery: bool):
+        self._check(self.lib.zkb_fr_convert_dev(self.h, d_data, n, int(to_montgomery)))
+
     # ---- bases / MSM
     def upload_bases(self, affine: bytes, g2=False) -> Bases:
         sz = 128 if g2 else 64
@@ -341,6 +365,12 @@ class Context:
         res = (C.c_double * 3)()
         self._check(self.lib.zkb_bench_int_pipe(self.h, iters, res))
         return {"imad_wide_per_s": res[0], "montmul_per_s": res[1], "sm_mhz": res[2]}
+
+
+def fr_root_of_unity(log_n: int, inverse=False) -> bytes:
+    out = C.create_string_buffer(32)
+    load_library().zkb_fr_root_of_unity(log_n, int(inverse), out)
+    return out.raw
 
 
 def synthetic_witness(log_n: int, w0: bytes, w1: bytes) -> bytes:

@@ -59,6 +59,25 @@ int zkb_fr_ntt(zkb_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, int cos
 int zkb_fr_ntt_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
                    int coset, int montgomery);
 
+/* Building blocks of the multi-GPU four-step NTT (one process per GPU; the transpose between the
+ * two steps is an NCCL all-to-all issued above this layer, eigen-zeth_b200/dist_ntt.py).  Device
+ * buffers, Montgomery form, asynchronous on the ctx stream.
+ *  - `batch` contiguous transforms of 2^log_size elements; tables (optional, batch * 2^log_size
+ *    entries, Montgomery) multiply the input / output element-wise; skip_ninv leaves 1/size out;
+ *  - permute: [a][b][c] -> [b][a][c] on 32-byte elements;
+ *  - table mode 0: out[hi*cols+lo] = scale * base^((row0+hi)*lo); mode 1: scale * base^((row0+hi) + lo*mul)
+ *    (base, scale canonical; output Montgomery);
+ *  - mul_sub: a[i] = a[i]*b[i] - c[i];   convert: canonical <-> Montgomery in place. */
+int zkb_fr_ntt_batch_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_size, uint64_t batch,
+                         int inverse, int skip_ninv, const void* d_pre_table, const void* d_post_table);
+int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, uint32_t b, uint32_t c);
+int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const uint8_t scale[32], uint64_t rows,
+                     uint64_t cols, uint64_t row0, uint64_t mul, int mode);
+int zkb_fr_mul_sub_dev(zkb_ctx* ctx, void* d_a, const void* d_b, const void* d_c, uint64_t n);
+int zkb_fr_convert_dev(zkb_ctx* ctx, void* d_data, uint64_t n, int to_montgomery);
+/* canonical 2^log_n-th root of unity of Fr (ark-ff TWO_ADIC_ROOT_OF_UNITY^(2^(28-log_n))) or its inverse */
+void zkb_fr_root_of_unity(uint32_t log_n, int inverse, uint8_t out[32]);
+
 /* ---- MSM  (serves the A/B1/L/H G1 MSMs and the B2 G2 MSM) ---------- */
 int zkb_bases_upload_g1(zkb_ctx* ctx, const uint8_t* affine, uint64_t n, zkb_bases** out);
 int zkb_bases_upload_g2(zkb_ctx* ctx, const uint8_t* affine, uint64_t n, zkb_bases** out);
@@ -108,7 +127,9 @@ int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t
                            zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]);
 void zkb_pk_free(zkb_pk* pk);
 /* borrowed handle to one query of the key: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 l_query,
- * 4 h_query (ark-groth16 ProvingKey field names); valid until zkb_pk_free; do not free it */
+ * 4 h_query (ark-groth16 ProvingKey field names); valid until zkb_pk_free; do not free it.
+ * l_query is stored at the full witness length: its first 2 entries (the instance variables, which
+ * ark-groth16 leaves out) are the point at infinity, so all witness MSMs share one scalar sort. */
 const zkb_bases* zkb_pk_query(const zkb_pk* pk, int which);
 /* full witness assignment z (2^log_n canonical Fr, z[0] = 1, z[1] = public input) from two seeds */
 int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
