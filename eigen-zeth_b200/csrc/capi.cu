@@ -802,6 +802,16 @@ int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, 
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
+int zkb_fr_gather_layout_dev(zkb_ctx* ctx, const void* d_full, void* d_out, uint32_t log_n, uint32_t low_bits,
+                             uint32_t world, uint32_t rank) {
+  ZKB_ENTER(ctx);
+  if (!d_full || !d_out || low_bits > log_n || world == 0 || rank >= world || ((1u << low_bits) % world))
+    return set_error(ctx, ZKB_EINVAL, "bad layout argument");
+  fr_gather_layout_launch(d_full, d_out, log_n, low_bits, world, rank, ctx->stream);
+  ctx->launches++;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
 int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const uint8_t scale[32], uint64_t rows,
                      uint64_t cols, uint64_t row0, uint64_t mul, int mode) {
   ZKB_ENTER(ctx);

@@ -38,6 +38,7 @@ struct zkb_pk {
   // point-range shard held by this key: query q covers [qfirst[q], qfirst[q] + qcount[q]) of the
   // full query (q = 0 a, 1 b_g1, 2 b_g2, 3 l, 4 h); world == 1 means the whole key
   uint32_t rank = 0, world = 1;
+  uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (dist_ntt.py)
   uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
 };
 
@@ -314,12 +315,19 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
 
 int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
                            zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]) {
+  return zkb_pk_synthetic_shard_ex(ctx, log_n, seed, rank, world, 0, out, vk_out);
+}
+
+int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
+                              uint32_t h_low_bits, zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]) {
   if (!ctx) return ZKB_EINVAL;
   BusyGuard guard(ctx);
   if (!guard.ok) return ZKB_EBUSY;
   if (!out || !vk_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   if (log_n < 3 || log_n > 26) return set_error(ctx, ZKB_EINVAL, "log_n must be in [3, 26]");
   if (world == 0 || rank >= world || world > 64) return set_error(ctx, ZKB_EINVAL, "bad rank / world");
+  if (h_low_bits && (h_low_bits >= log_n || ((1ull << h_low_bits) % world) || (world & (world - 1))))
+    return set_error(ctx, ZKB_EINVAL, "bad h layout");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   zkb_pk* pk = new (std::nothrow) zkb_pk();
   if (!pk) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
@@ -334,6 +342,7 @@ int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t
     pk->ncons = cs.ncons;
     pk->rank = rank;
     pk->world = world;
+    pk->h_low_bits = h_low_bits;
     const uint64_t qlen[5] = {m, m, m, m, n - 1};   // l_query is stored padded to m (see below)
     for (int q = 0; q < 5; q++) {
       uint64_t base = qlen[q] / world, rem = qlen[q] % world;
@@ -403,7 +412,22 @@ int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t
       canon_into(tp, sc, i);
       tp = tp * tau;
     }
-    if ((rc = make_query(ctx, sc, pk->qfirst[4], pk->qcount[4], 0, &pk->h_query))) throw rc;
+    if (h_low_bits) {
+      // h_query in the output layout of the distributed NTT: local [low_loc][high] holds the base
+      // of coefficient (rank*lows + low_loc) + (high << h_low_bits); index n-1 (h has n-1
+      // coefficients) is the point at infinity
+      canon_into(HFr::zero(), sc, n - 1);
+      const uint64_t lows = (1ull << h_low_bits) / world, highs = n >> h_low_bits;
+      std::vector<uint64_t> sel(4 * lows * highs);
+      for (uint64_t lo = 0; lo < lows; lo++)
+        for (uint64_t hi = 0; hi < highs; hi++) {
+          uint64_t k = (rank * lows + lo) + (hi << h_low_bits);
+          std::memcpy(&sel[4 * (lo * highs + hi)], &sc[4 * k], 32);
+        }
+      pk->qfirst[4] = 0;
+      pk->qcount[4] = lows * highs;
+      if ((rc = make_query(ctx, sel, 0, pk->qcount[4], 0, &pk->h_query))) throw rc;
+    } else if ((rc = make_query(ctx, sc, pk->qfirst[4], pk->qcount[4], 0, &pk->h_query))) throw rc;
     if (ctx->pk_precompute) {
       zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
       for (zkb_bases* q : qs)
@@ -574,6 +598,46 @@ static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[
   return ZKB_OK;
 }
 
+// witness -> a, b, c evaluation vectors (Montgomery, natural order) in pk->d_a / d_b / d_c
+static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness) {
+  const uint64_t n = pk->n, m = pk->m;
+  cudaStream_t st = ctx->stream;
+  ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
+  ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st));
+  const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
+  fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
+  void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
+  for (int k = 0; k < 3; k++)
+    r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
+                                           (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
+                                           (Fr*)outs[k], pk->ncons, n, k == 0, 2);
+  ctx->launches += 4;
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+// witness MSMs over pk's ranges + H MSM with h taken from d_h (canonical, pk's local h order)
+static int prove_msm_only_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, uint8_t* results_out) {
+  char* res = (char*)pk->d_results;
+  const char* z = (const char*)pk->d_z;
+  const zkb_bases* qs[4] = {pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query};
+  void* outs4[4] = {res, res + 64, res + 256, res + 128};
+  int rc = msm_exec_multi(ctx, qs, 4, z + 32 * pk->qfirst[0], 0, pk->qcount[0], outs4, nullptr);
+  if (rc) return rc;
+  if ((rc = msm_exec(ctx, pk->h_query, 0, d_h, pk->qcount[4], res + 320))) return rc;
+  uint32_t bad_flag = 0;
+  ZKB_CUDA(ctx, cudaMemcpyAsync(results_out, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(&bad_flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZKB_CUDA(ctx, cudaGetLastError());
+  if (bad_flag & 1) {
+    cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream);
+    return set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in the witness");
+  }
+  return ZKB_OK;
+}
+
 #define ZKB_PK_ENTER(ctx, pk)                                                             \
   if (!(ctx)) return ZKB_EINVAL;                                                          \
   BusyGuard guard(ctx);                                                                   \
@@ -607,6 +671,23 @@ int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wit
   ZKB_PK_ENTER(ctx, pk);
   if (!witness || !partial_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   return prove_msm_phase(ctx, pk, witness, timings_opt, nullptr, partial_out);
+}
+
+int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, void* d_abc_out[3]) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!witness || !d_abc_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  int rc = prove_witness_phase(ctx, pk, witness);
+  d_abc_out[0] = pk->d_a;
+  d_abc_out[1] = pk->d_b;
+  d_abc_out[2] = pk->d_c;
+  return rc;
+}
+
+int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
+                        uint8_t partial_out[ZKB_INTERMEDIATE_BYTES]) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!d_h || !partial_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  return prove_msm_only_phase(ctx, pk, d_h, partial_out);
 }
 
 int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],

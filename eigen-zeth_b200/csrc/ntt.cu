@@ -334,6 +334,19 @@ __global__ void fr_permute_kernel(const uint4* __restrict__ in, uint4* __restric
   out[q] = in[(((uint64_t(a) * B + b) * C + c) << 1) | (q & 1)];
 }
 
+// layout-d block of rank g out of a natural-order vector (dist_ntt.py):
+// out[low_loc * H + high] = full[(g * lows + low_loc) + (high << d)],  H = n >> d
+__global__ void fr_gather_layout_kernel(const uint4* __restrict__ full, uint4* __restrict__ out,
+                                        uint32_t log_n, uint32_t d, uint32_t lows, uint32_t low0) {
+  uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  const uint32_t hbits = log_n - d;
+  if (q >= (uint64_t(lows) << hbits) * 2) return;
+  uint64_t pos = q >> 1;
+  uint64_t low_loc = pos >> hbits, high = pos & ((1ull << hbits) - 1);
+  uint64_t src = (low0 + low_loc) + (high << d);
+  out[q] = full[(src << 1) | (q & 1)];
+}
+
 __global__ void fr_table_kernel(Fr* out, Fr base, Fr c, uint64_t rows, uint64_t cols, uint64_t row0,
                                 uint64_t mul, int mode) {
   uint64_t pos = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -393,6 +406,16 @@ void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32
   uint32_t blocks = uint32_t((total + 255) / 256);
   if (blocks)
     fr_permute_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), A, B, C);
+}
+
+void fr_gather_layout_launch(const void* full, void* out, uint32_t log_n, uint32_t d, uint32_t world,
+                             uint32_t rank, cudaStream_t s) {
+  uint32_t lows = (1u << d) / world;
+  uint64_t total = (uint64_t(lows) << (log_n - d)) * 2;
+  uint32_t blocks = uint32_t((total + 255) / 256);
+  if (blocks)
+    fr_gather_layout_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(full),
+                                                   reinterpret_cast<uint4*>(out), log_n, d, lows, rank * lows);
 }
 
 void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t rows, uint64_t cols,

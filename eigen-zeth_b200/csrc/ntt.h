@@ -45,6 +45,8 @@ void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32
 //   mode 1: out[pos] = c * base^{(row0 + hi) + lo * mul}      (coset powers at global index k1 + N1 k2)
 void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t rows, uint64_t cols,
                      uint64_t row0, uint64_t mul, int mode, cudaStream_t s);
+void fr_gather_layout_launch(const void* full, void* out, uint32_t log_n, uint32_t d, uint32_t world,
+                             uint32_t rank, cudaStream_t s);
 // a[i] = a[i] * b[i] - c[i]
 void fr_mul_sub_launch(void* a, const void* b, const void* c, uint64_t n, cudaStream_t s);
 

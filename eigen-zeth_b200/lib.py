@@ -23,7 +23,8 @@ EXPORTS = [
     "zkb_bases_precompute", "zkb_bases_window",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_free", "zkb_pk_query",
-    "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
+    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
@@ -91,6 +92,10 @@ def load_library() -> C.CDLL:
     if hasattr(lib, "zkb_pk_synthetic"):
         lib.zkb_pk_synthetic.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
         lib.zkb_pk_synthetic_shard.argtypes = [vp, u32, u64, u32, u32, C.POINTER(vp), vp]
+        lib.zkb_pk_synthetic_shard_ex.argtypes = [vp, u32, u64, u32, u32, u32, C.POINTER(vp), vp]
+        lib.zkb_groth16_witness_dev.argtypes = [vp, vp, vp, C.POINTER(vp)]
+        lib.zkb_groth16_msm_dev.argtypes = [vp, vp, vp, vp]
+        lib.zkb_fr_gather_layout_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32]
         lib.zkb_groth16_prove_partial.argtypes = [vp, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_assemble.argtypes = [vp, vp, u8p, u8p, u8p, vp]
         lib.zkb_pk_free.argtypes = [vp]
@@ -310,11 +315,30 @@ class Context:
         self._check(self.lib.zkb_pk_synthetic(self.h, log_n, seed, C.byref(h), vk))
         return ProvingKey(self, h, vk.raw, log_n)
 
-    def pk_synthetic_shard(self, log_n: int, seed: int, rank: int, world: int) -> ProvingKey:
+    def pk_synthetic_shard(self, log_n: int, seed: int, rank: int, world: int, h_low_bits: int = 0) -> ProvingKey:
         h = C.c_void_p()
         vk = C.create_string_buffer(VK_BYTES)
-        self._check(self.lib.zkb_pk_synthetic_shard(self.h, log_n, seed, rank, world, C.byref(h), vk))
+        self._check(self.lib.zkb_pk_synthetic_shard_ex(self.h, log_n, seed, rank, world, h_low_bits, C.byref(h), vk))
         return ProvingKey(self, h, vk.raw, log_n)
+
+    def groth16_witness_dev(self, pk: ProvingKey, witness):
+        """H2D + R1CS products; returns the device pointers of the a, b, c evaluation vectors."""
+        ptrs = (C.c_void_p * 3)()
+        if isinstance(witness, (bytes, bytearray)):
+            wbuf = C.create_string_buffer(bytes(witness), len(witness))
+            wptr = C.cast(wbuf, C.c_void_p)
+        else:
+            wptr = C.c_void_p(int(witness))
+        self._check(self.lib.zkb_groth16_witness_dev(self.h, pk.handle, wptr, ptrs))
+        return [int(p) for p in ptrs]
+
+    def groth16_msm_dev(self, pk: ProvingKey, d_h: int) -> bytes:
+        out = C.create_string_buffer(INTERMEDIATE_BYTES)
+        self._check(self.lib.zkb_groth16_msm_dev(self.h, pk.handle, d_h, out))
+        return out.raw
+
+    def fr_gather_layout_dev(self, d_full: int, d_out: int, log_n: int, low_bits: int, world: int, rank: int):
+        self._check(self.lib.zkb_fr_gather_layout_dev(self.h, d_full, d_out, log_n, low_bits, world, rank))
 
     def groth16_prove_partial(self, pk: ProvingKey, witness):
         """-> (384-byte partial MSM sums over this key's point ranges, timings)"""

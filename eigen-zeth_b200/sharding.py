@@ -72,3 +72,56 @@ def groth16_prove_sharded(ctx, pk, witness, r: bytes, s: bytes, world: int):
         parts = [bytes(row.cpu().numpy()) for row in gather_partials(t, world)]
     sums = combine_partial_sums(parts, lambda pts, g2: ctx.point_sum(pts, g2=g2))
     return ctx.groth16_assemble(pk, sums, r, s), timings
+
+
+class FourStepProver:
+    """Groth16 prove over `world` ranks with the witness map distributed too: the seven NTTs run as
+    four-step transforms (one NCCL all-to-all each, dist_ntt.py), every MSM is sharded by points,
+    and h never leaves the layout the last transform produced it in (the key's h_query shard is
+    stored in that layout).  One instance per rank; `pk` must come from
+    ctx.pk_synthetic_shard(log_n, seed, rank, world, h_low_bits=prover.h_low_bits)."""
+
+    def __init__(self, ctx, log_n: int, world: int, rank: int):
+        import torch
+        from .dist_ntt import FourStepNtt, COSET_GEN, R
+        self.ctx, self.log_n, self.world, self.rank = ctx, log_n, world, rank
+        self.ntt = FourStepNtt(ctx, log_n, world, rank)
+        self.d0 = log_n // 2                 # layout of the evaluation vectors
+        self.d1 = log_n - self.d0            # layout after one transform = layout of h
+        n = 1 << log_n
+        zinv = pow((pow(COSET_GEN, n, R) - 1) % R, R - 2, R)
+        self.t_coset = self.ntt.index_power_table(self.d1, COSET_GEN)
+        self.t_uncoset = self.ntt.index_power_table(self.d1, pow(COSET_GEN, R - 2, R), zinv)
+        self.bufs = [torch.empty(self.ntt.n_loc * 32, dtype=torch.uint8, device=self.ntt.device) for _ in range(3)]
+
+    @property
+    def h_low_bits(self) -> int:
+        return self.d1
+
+    def witness_map(self, pk, witness):
+        """-> torch tensor with this rank's h coefficients (canonical) in layout d1."""
+        ctx, nt, L = self.ctx, self.ntt, self.log_n
+        ptrs = ctx.groth16_witness_dev(pk, witness)
+        for p, buf in zip(ptrs, self.bufs):
+            ctx.fr_gather_layout_dev(p, buf.data_ptr(), L, self.d0, self.world, self.rank)
+        for buf in self.bufs:
+            nt.transform(buf, self.d0, inverse=True, post=self.t_coset)      # coefficients * g^k
+        for buf in self.bufs:
+            nt.transform(buf, self.d1, inverse=False)                        # evaluations on the coset
+        a, b, c = self.bufs
+        ctx.fr_mul_sub_dev(a.data_ptr(), b.data_ptr(), c.data_ptr(), nt.n_loc)
+        nt.transform(a, self.d0, inverse=True, post=self.t_uncoset)          # h * 1  (g^-k / Z folded)
+        ctx.fr_convert_dev(a.data_ptr(), nt.n_loc, False)
+        return a
+
+    def prove(self, pk, witness, r: bytes, s: bytes) -> bytes:
+        import torch
+        h = self.witness_map(pk, witness)
+        partial = self.ctx.groth16_msm_dev(pk, h.data_ptr())
+        if self.world == 1:
+            parts = [partial]
+        else:
+            t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(self.ntt.device)
+            parts = [bytes(row.cpu().numpy()) for row in gather_partials(t, self.world)]
+        sums = combine_partial_sums(parts, lambda pts, g2: self.ctx.point_sum(pts, g2=g2))
+        return self.ctx.groth16_assemble(pk, sums, r, s)

@@ -71,6 +71,9 @@ int zkb_fr_ntt_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, 
 int zkb_fr_ntt_batch_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_size, uint64_t batch,
                          int inverse, int skip_ninv, const void* d_pre_table, const void* d_post_table);
 int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, uint32_t b, uint32_t c);
+/* this rank's layout-d block of a natural-order device vector (dist_ntt.py "layout d") */
+int zkb_fr_gather_layout_dev(zkb_ctx* ctx, const void* d_full, void* d_out, uint32_t log_n, uint32_t low_bits,
+                             uint32_t world, uint32_t rank);
 int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const uint8_t scale[32], uint64_t rows,
                      uint64_t cols, uint64_t row0, uint64_t mul, int mode);
 int zkb_fr_mul_sub_dev(zkb_ctx* ctx, void* d_a, const void* d_b, const void* d_c, uint64_t n);
@@ -125,6 +128,10 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
  * this GPU (one process per GPU; the MSM partial sums are combined above this layer) */
 int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
                            zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]);
+/* as above, with h_query held in the output layout of the four-step NTT: local [low_loc][high]
+ * is the base of coefficient (rank * 2^h_low_bits / world + low_loc) + (high << h_low_bits) */
+int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
+                              uint32_t h_low_bits, zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]);
 void zkb_pk_free(zkb_pk* pk);
 /* borrowed handle to one query of the key: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 l_query,
  * 4 h_query (ark-groth16 ProvingKey field names); valid until zkb_pk_free; do not free it.
@@ -148,6 +155,13 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
  * slot (zkb_g1_sum / zkb_g2_sum after an all-gather) and any rank assembles the proof */
 int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
                               uint8_t partial_out[ZKB_INTERMEDIATE_BYTES], zkb_prove_timings* timings_opt);
+/* the prover split for the distributed witness map: (1) witness -> A z, B z, C z evaluation vectors
+ * (device, Montgomery, natural order; pointers returned in d_abc_out, owned by the key);
+ * (2) ... the caller runs the NTT chain (dist_ntt.py) ...; (3) the five MSMs with h read from d_h
+ * (canonical, in the key's local h order) -> this rank's 384-byte partial sums */
+int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, void* d_abc_out[3]);
+int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
+                        uint8_t partial_out[ZKB_INTERMEDIATE_BYTES]);
 int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
                          const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES]);
 /* CPU pairing check e(A,B) = e(alpha,beta) e(ic0 + x*ic1, gamma) e(C,delta); 0 = valid,
