@@ -300,7 +300,7 @@ def main():
                 "ms": t_ms, "gelem_s": n / (t_ms * 1e-3) / 1e9,
                 "frac_int_pipe": 136 * (n // 2) * log_n / (t_ms * 1e-3) / pipe["imad_wide_per_s"],
                 "frac_hbm": 128 * n / (t_ms * 1e-3) / 1e9 / hbm_peak}
-        ctx.set("ntt_full_twiddles", 0)
+        ctx.set("ntt_full_twiddles", 1)
         line["ntt_2^%d" % log_n] = ntt
         del x
         try:

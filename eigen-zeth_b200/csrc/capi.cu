@@ -194,7 +194,7 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
   const uint64_t n = 1ull << log_n;
   const uint64_t total = n * batch;
   if ((total >> 11) * 8 >= (1ull << 31)) return set_error(ctx, ZKB_EINVAL, "batch too large");
-  const bool use_full = P > 1 && ctx->ntt_full_twiddles && !skip_ninv;
+  const bool use_full = P > 1 && ctx->ntt_full_twiddles && !(inverse && skip_ninv);   // full tables fold 1/n
   if (use_full && (rc = ensure_full_tables(ctx, d, inverse))) return rc;
   if (inverse && P == 1 && !post_scale && !skip_ninv) {
     if (batch != 1) return set_error(ctx, ZKB_EINVAL, "batched single-pass inverse needs an explicit scale table");

@@ -77,7 +77,7 @@ struct zkb_ctx {
   std::string err;
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   int64_t msm_window = 0;
-  int64_t ntt_full_twiddles = 0;
+  int64_t ntt_full_twiddles = 1;           // n-entry inter-pass twiddle tables (1 modmul instead of 2)
   int64_t msm_profile = 0;
   int64_t msm_host_chunks = 0;             // 0 = auto
   int64_t pk_precompute = 1;               // proving-key queries carry precomputed window multiples

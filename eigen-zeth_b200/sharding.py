@@ -114,14 +114,30 @@ class FourStepProver:
         ctx.fr_convert_dev(a.data_ptr(), nt.n_loc, False)
         return a
 
-    def prove(self, pk, witness, r: bytes, s: bytes) -> bytes:
+    def prove(self, pk, witness, r: bytes, s: bytes, timings: dict | None = None) -> bytes:
+        """`timings` (optional) receives wall-clock seconds per stage; asking for it inserts stream
+        synchronisations between the stages."""
+        import time
         import torch
+
+        def lap(name, t0):
+            if timings is not None:
+                self.ctx.sync()
+                timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t0 = time.perf_counter()
         h = self.witness_map(pk, witness)
+        t0 = lap("witness_map", t0)
         partial = self.ctx.groth16_msm_dev(pk, h.data_ptr())
+        t0 = lap("msm", t0)
         if self.world == 1:
             parts = [partial]
         else:
             t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(self.ntt.device)
             parts = [bytes(row.cpu().numpy()) for row in gather_partials(t, self.world)]
         sums = combine_partial_sums(parts, lambda pts, g2: self.ctx.point_sum(pts, g2=g2))
-        return self.ctx.groth16_assemble(pk, sums, r, s)
+        t0 = lap("gather_combine", t0)
+        proof = self.ctx.groth16_assemble(pk, sums, r, s)
+        lap("assemble", t0)
+        return proof

@@ -18,6 +18,13 @@ def test_ntt_matches_oracle(ctx, log_n):
     assert fr_list(ctx.fr_ntt(buf, inverse=True)) == o.ntt(v, inverse=True)
     assert fr_list(ctx.fr_ntt(buf, coset=True)) == o.coset_ntt(v)
     assert fr_list(ctx.fr_ntt(buf, inverse=True, coset=True)) == o.coset_intt(v)
+    if log_n >= 9:          # multi-pass sizes: also the two-level inter-pass twiddle path
+        ctx.set("ntt_full_twiddles", 0)
+        try:
+            assert fr_list(ctx.fr_ntt(buf)) == o.ntt(v)
+            assert fr_list(ctx.fr_ntt(buf, inverse=True)) == o.ntt(v, inverse=True)
+        finally:
+            ctx.set("ntt_full_twiddles", 1)
 
 
 @pytest.mark.parametrize("full", [0, 1])
@@ -48,7 +55,7 @@ def test_ntt_properties_large(ctx, log_n, full):
         for k in (0, 1, 2, 3, n // 2 + 1, n - 1, 77 % n):
             assert fr_list(fd[32 * k: 32 * k + 32]) == [pow(w, k, o.R)]
     finally:
-        ctx.set("ntt_full_twiddles", 0)
+        ctx.set("ntt_full_twiddles", 1)
 
 
 def test_ntt_rejects_bad_input(ctx, zkb):

@@ -74,6 +74,19 @@ def main():
     proof4b = prover.prove(fpk, w, r, s)
     dist.barrier()
     dt = time.perf_counter() - t0
+    if os.environ.get("ZKB_STAGES"):
+        glog = int(os.environ["ZKB_STAGES"])
+        p2 = FourStepProver(ctx, glog, world, rank)
+        k2 = ctx.pk_synthetic_shard(glog, seed, rank, world, h_low_bits=p2.h_low_bits)
+        w2 = z.synthetic_witness(glog, (5).to_bytes(32, "little"), (7).to_bytes(32, "little"))
+        wt = torch.frombuffer(bytearray(w2), dtype=torch.uint8).pin_memory()
+        for i in range(3):
+            tm = {}
+            dist.barrier()
+            p2.prove(k2, wt.data_ptr(), r, s, timings=tm)
+        if rank == 0:
+            print("stages 2^%d world=%d:" % (glog, world), {k: round(v * 1e3, 2) for k, v in tm.items()}, flush=True)
+        k2.free()
     if rank == 0:
         g1, g2 = proof == want, proof4 == want and proof4b == want
         ok &= g1 and g2
