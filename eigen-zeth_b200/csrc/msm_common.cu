@@ -76,12 +76,20 @@ size_t msm_sort_temp_bytes(uint64_t m, int end_bit) {
 int msm_auto_window(uint64_t n, bool precomputed) {
   int log_n = 0;
   while ((1ull << log_n) < n) log_n++;
-  // classic: W bucket sets, keep buckets << points.  precomputed: ONE bucket set shared by all
-  // windows, so the width can grow until the bucket reduction (2 adds per bucket) shows.
-  int c = precomputed ? log_n - 4 : log_n - 6;
-  int lo = precomputed ? 8 : 4, hi = precomputed ? 20 : 16;
-  if (c < lo) c = lo;
-  if (c > hi) c = hi;
+  if (precomputed) {
+    // ONE bucket set shared by all windows: the width can grow until the bucket reduction
+    // (2 adds per bucket) shows.  Only the smallest c of each window count ceil(255/c) is useful.
+    // Calibrated on B200 (tools/tune_window.py, profiles/r01_tune_window.json).
+    if (log_n <= 14) return 11;   // 24 windows
+    if (log_n <= 16) return 15;   // 17
+    if (log_n <= 19) return 17;   // 15
+    if (log_n <= 23) return 20;   // 13
+    return 23;                    // 12
+  }
+  // classic: one bucket set per window, keep buckets << points
+  int c = log_n - 6;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
   return c;
 }
 
