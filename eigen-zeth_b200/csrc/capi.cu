@@ -287,8 +287,8 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, boo
   ZKB_CUDA(ctx, s.part1_pts.ensure(2ull * p.l1_threads * p.point_bytes));
   ZKB_CUDA(ctx, s.part2_keys.ensure(2ull * p.l2_threads * 4));
   ZKB_CUDA(ctx, s.part2_pts.ensure(2ull * p.l2_threads * p.point_bytes));
-  ZKB_CUDA(ctx, s.group_sums.ensure((uint64_t(p.n_groups) + 64ull * p.n_sets) * p.point_bytes));
-  ZKB_CUDA(ctx, s.window_sums.ensure(uint64_t(p.n_sets) * p.point_bytes));
+  ZKB_CUDA(ctx, s.group_sums.ensure((p.red_run_total + uint64_t(p.n_sets) * ((p.half + 15) / 16 + 64)) * p.point_bytes));
+  ZKB_CUDA(ctx, s.window_sums.ensure(uint64_t(p.red_levels + 2) * p.n_sets * p.point_bytes));
   ZKB_CUDA(ctx, s.result_xyzz.ensure(p.point_bytes));
   ZKB_CUDA(ctx, s.result_affine.ensure(p.point_bytes / 2));
   b->keys_in = (uint32_t*)s.keys_in.p;

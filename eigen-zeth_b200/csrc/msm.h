@@ -19,9 +19,8 @@ struct MsmPlan {
   uint32_t l1_threads;      // chunks of the level-1 walk
   uint32_t l2_len;          // chunk length of the level-2 walk
   uint32_t l2_threads;
-  uint32_t gsize;           // buckets per reduce group
-  uint32_t groups_per_win;
-  uint32_t n_groups;
+  uint32_t red_levels;      // bucket-reduction levels (1, or 2 for >= 2^20 buckets per set)
+  uint64_t red_run_total;   // points of run output over all levels and sets
   size_t point_bytes;       // sizeof(XYZZ)
   size_t sort_temp_bytes;
 };
@@ -37,8 +36,8 @@ struct MsmBuffers {
   void* part1_pts;
   uint32_t* part2_keys;     // 2 * l2_threads
   void* part2_pts;
-  void* group_sums;         // n_groups XYZZ
-  void* window_sums;        // n_sets XYZZ
+  void* group_sums;         // reduction scratch (see msm_tail_t)
+  void* window_sums;        // (red_levels + 2) * n_sets XYZZ
   void* result_xyzz;        // 1 XYZZ (Montgomery)
   void* result_affine;      // 1 affine, canonical little-endian
   cudaEvent_t* ev;          // optional 6 profiling events: start, digits, sort, L1, L2+finish, tail

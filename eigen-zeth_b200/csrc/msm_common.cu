@@ -83,7 +83,7 @@ int msm_auto_window(uint64_t n, bool precomputed) {
     if (log_n <= 14) return 11;   // 24 windows
     if (log_n <= 16) return 15;   // 17
     if (log_n <= 19) return 17;   // 15
-    if (log_n <= 23) return 20;   // 13
+    if (log_n <= 22) return 20;   // 13
     return 23;                    // 12
   }
   // classic: one bucket set per window, keep buckets << points
@@ -114,9 +114,14 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
   p.l1_threads = uint32_t(t1);
   p.l2_len = 32;
   p.l2_threads = (2 * p.l1_threads + p.l2_len - 1) / p.l2_len;
-  p.gsize = p.half < 16 ? p.half : 16;
-  p.groups_per_win = p.half / p.gsize;
-  p.n_groups = p.groups_per_win * p.n_sets;
+  // one 16-way level first only when the bucket array is huge (msm_impl.cuh, section 6)
+  p.red_levels = p.half >= (1u << 20) ? 2 : 1;
+  p.red_run_total = 0;
+  for (uint32_t l = 0, cnt = p.half; l < p.red_levels; l++) {
+    uint32_t groups = (cnt + 15) / 16;
+    p.red_run_total += uint64_t(groups) * p.n_sets;
+    cnt = groups;
+  }
   p.point_bytes = is_g2 ? 256 : 128;
   p.sort_temp_bytes = msm_sort_temp_bytes(p.m, p.key_bits);
   return p;

@@ -15,9 +15,9 @@
 //                        whatever the bucket-size distribution is.
 //   4. accumulate L2     the same chunked walk over the partial list (XYZZ + XYZZ).
 //   5. finish            one thread per remaining run.
-//   6. bucket reduce     per group of 32 buckets: running sums, then weight by the group base.
-//   7. window sum        tree reduction of the group sums of each window.
-//   8. Horner            sum_w 2^{cw} S_w, conversion to affine, out of Montgomery form.
+//   6. bucket reduce     levels of 16-way running sums (no scalar multiplications, see below).
+//   7. window sum        tree reduction of each level's weighted sums.
+//   8. Horner            over the reduce levels (x16) and the bucket sets (x2^c), to affine.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -158,24 +158,37 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restr
 }
 
 // ---------------------------------------------------------------- 6. bucket reduce
-// group of `gsize` consecutive buckets of one window -> sum_j (base + j + 1) * B_{base + j}
+// sum_j (j+1) B_j without any scalar multiplication: with zero-based weights W0(B) = sum_j j B_j
+// and groups of 16,  W0(B) = sum_g w0_g + 16 * W0(run),  w0_g = sum_t t B_{16g+t},
+// run_g = sum_t B_{16g+t}.  One level = one launch: thread g turns 16 inputs into (run_g, w0_g)
+// with 31 additions; the runs are the next level's input (16x fewer), the w0's of a level are
+// summed by the window-sum kernel, and the answer is  S + sum_l 16^l W_l  (S = sum of the runs of
+// the last level).  Each level is a latency-bound launch, so only arrays of >= 2^20 buckets take a
+// 16-way level first; the (last) level then folds 16 g run_g in with a small scalar multiplication.
+constexpr uint32_t kRedGroup = 16;
+
 template <class F>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(
-    const XYZZ<F>* __restrict__ buckets, uint32_t half, uint32_t gsize, uint32_t groups_per_win,
-    uint32_t n_groups, XYZZ<F>* __restrict__ group_sums) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  uint32_t w = g / groups_per_win;
-  uint32_t gi = g - w * groups_per_win;
-  uint32_t base = gi * gsize;
-  const XYZZ<F>* b = buckets + uint64_t(w) * half + base;
-  XYZZ<F> run = XYZZ<F>::infinity(), wsum = XYZZ<F>::infinity();
-  for (int j = int(gsize) - 1; j >= 0; j--) {
-    run.add(XYZZ<F>::load(b + j));
-    wsum.add(run);
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const XYZZ<F>* __restrict__ in,
+                                                               uint32_t count, uint32_t groups,
+                                                               uint32_t n_sets, XYZZ<F>* __restrict__ run_out,
+                                                               XYZZ<F>* __restrict__ w0_out, int last_level) {
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= groups * n_sets) return;
+  uint32_t set = gid / groups, g = gid - set * groups;
+  const XYZZ<F>* b = in + uint64_t(set) * count + uint64_t(g) * kRedGroup;
+  uint32_t avail = count - g * kRedGroup;
+  if (avail > kRedGroup) avail = kRedGroup;
+  XYZZ<F> r = XYZZ<F>::infinity(), w = XYZZ<F>::infinity();
+  for (int t = int(avail) - 1; t >= 1; t--) {
+    r.add(XYZZ<F>::load(b + t));
+    w.add(r);
   }
-  if (base) wsum.add(mul_small(run, base));
-  wsum.store(group_sums + g);
+  r.add(XYZZ<F>::load(b));
+  // the last level closes the recursion with one small scalar multiplication per group:
+  // sum_j j x_j over the whole array = sum_g (w0_g + 16 g run_g)
+  if (last_level && g) w.add(mul_small(r, g * kRedGroup));
+  r.store(run_out + gid);
+  w.store(w0_out + gid);
 }
 
 // ---------------------------------------------------------------- 7. window sum
@@ -207,16 +220,31 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __re
 }
 
 // ---------------------------------------------------------------- 8. Horner + output
+// per set: S + sum_l 16^l W_l (Horner over the reduce levels, 4 doublings each), then Horner over
+// the sets with c doublings each.  wl is [level][set]; s_tot is [set].
 // result (Montgomery XYZZ, 4*sizeof(F) bytes) and canonical affine (2*sizeof(F) bytes)
 template <class F>
-__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ window_sums, uint32_t nwin,
-                                  uint32_t c, XYZZ<F>* __restrict__ out_xyzz,
+__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ wl, const XYZZ<F>* __restrict__ s_tot,
+                                  uint32_t levels, uint32_t n_sets, uint32_t c,
+                                  XYZZ<F>* __restrict__ set_sums, XYZZ<F>* __restrict__ out_xyzz,
                                   Affine<F>* __restrict__ out_affine) {
-  if (threadIdx.x || blockIdx.x) return;
-  XYZZ<F> acc = XYZZ<F>::load(window_sums + (nwin - 1));
-  for (int w = int(nwin) - 2; w >= 0; w--) {
+  const uint32_t t = threadIdx.x;
+  if (blockIdx.x) return;
+  if (t < n_sets) {
+    XYZZ<F> acc = XYZZ<F>::load(wl + uint64_t(levels - 1) * n_sets + t);
+    for (int l = int(levels) - 2; l >= 0; l--) {
+      for (int k = 0; k < 4; k++) acc = acc.dbl();
+      acc.add(XYZZ<F>::load(wl + uint64_t(l) * n_sets + t));
+    }
+    acc.add(XYZZ<F>::load(s_tot + t));
+    acc.store(set_sums + t);
+  }
+  __syncthreads();
+  if (t) return;
+  XYZZ<F> acc = XYZZ<F>::load(set_sums + (n_sets - 1));
+  for (int w = int(n_sets) - 2; w >= 0; w--) {
     for (uint32_t i = 0; i < c; i++) acc = acc.dbl();
-    acc.add(XYZZ<F>::load(window_sums + w));
+    acc.add(XYZZ<F>::load(set_sums + w));
   }
   acc.store(out_xyzz);
   Affine<F> a = acc.to_affine();
@@ -297,24 +325,46 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
 }
 
 // bucket sums -> one point (Montgomery XYZZ + canonical affine)
+// scratch layout in b.group_sums (points): [runs of all levels][w0 of one level][stage 64*n_sets]
+// b.window_sums: [levels][n_sets] W_l, [n_sets] S, [n_sets] set sums
 template <class F>
 void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
   using P = XYZZ<F>;
-  msm_bucket_reduce_kernel<F><<<(p.n_groups + 127) / 128, 128, 0, s>>>(
-      reinterpret_cast<const P*>(b.buckets), p.half, p.gsize, p.groups_per_win, p.n_groups,
-      reinterpret_cast<P*>(b.group_sums));
-  // two-stage sum of the group results of every set
-  const uint32_t slices = p.groups_per_win >= 4096 ? 64 : (p.groups_per_win >= 256 ? 8 : 1);
-  P* stage = reinterpret_cast<P*>(b.group_sums) + p.n_groups;     // scratch behind the group sums
-  msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(
-      reinterpret_cast<const P*>(b.group_sums), p.groups_per_win, slices,
-      slices > 1 ? stage : reinterpret_cast<P*>(b.window_sums));
-  if (slices > 1)
-    msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(
-        stage, slices, 1, reinterpret_cast<P*>(b.window_sums));
-  msm_horner_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const P*>(b.window_sums), p.n_sets, p.c,
-                                        reinterpret_cast<P*>(b.result_xyzz),
-                                        reinterpret_cast<Affine<F>*>(b.result_affine));
+  P* scratch = reinterpret_cast<P*>(b.group_sums);
+  P* wl = reinterpret_cast<P*>(b.window_sums);
+  const P* in = reinterpret_cast<const P*>(b.buckets);
+  uint32_t count = p.half;
+  P* run_cursor = scratch;
+  P* w0 = scratch + p.red_run_total;
+  P* stage = w0 + uint64_t(p.n_sets) * ((p.half + kRedGroup - 1) / kRedGroup);
+  uint32_t groups = 0;
+  for (uint32_t l = 0; l < p.red_levels; l++) {
+    groups = (count + kRedGroup - 1) / kRedGroup;
+    uint32_t threads = groups * p.n_sets;
+    const int last = l + 1 == p.red_levels;
+    msm_reduce_level_kernel<F><<<(threads + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
+    // W_l[set] = sum of this level's w0 (two-stage when there are many)
+    const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
+    P* wl_out = wl + uint64_t(l) * p.n_sets;
+    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(w0, groups, slices,
+                                                                             slices > 1 ? stage : wl_out);
+    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, wl_out);
+    in = run_cursor;
+    run_cursor += uint64_t(threads);
+    count = groups;
+  }
+  // S[set] = sum of the runs of the last level
+  P* s_tot = wl + uint64_t(p.red_levels) * p.n_sets;
+  {
+    const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
+    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(in, groups, slices,
+                                                                             slices > 1 ? stage : s_tot);
+    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, s_tot);
+  }
+  msm_horner_kernel<F><<<1, 128, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,
+                                         wl + uint64_t(p.red_levels + 1) * p.n_sets,
+                                         reinterpret_cast<P*>(b.result_xyzz),
+                                         reinterpret_cast<Affine<F>*>(b.result_affine));
   if (b.ev) cudaEventRecord(b.ev[5], s);
 }
 
