@@ -291,20 +291,20 @@ int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1
   const uint64_t m = 1ull << log_n;
   HFr a, b;
   if (!HFr::from_bytes(w0, &a) || !HFr::from_bytes(w1, &b)) return ZKB_EINVAL;
-  std::vector<HFr> z;
-  try {
-    z.assign(m, HFr::zero());
-  } catch (...) {
-    return ZKB_ENOMEM;
-  }
   HFr small[8];
   for (int i = 0; i < 8; i++) small[i] = HFr::from_u64(i);
-  z[0] = HFr::one();
-  z[2] = a;
-  z[3] = b;
-  for (uint64_t j = 0; j + 4 < m; j++) z[j + 4] = (z[j + 2] + small[j % 7 + 1]) * z[j + 3];
-  z[1] = z[m - 1] * z[m - 2];
-  for (uint64_t i = 0; i < m; i++) z[i].to_bytes(z_out + 32 * i);
+  // z[j+4] = (z[j+2] + (j%7+1)) * z[j+3]: a two-term recurrence, streamed straight into the output
+  HFr::one().to_bytes(z_out);
+  a.to_bytes(z_out + 64);
+  b.to_bytes(z_out + 96);
+  HFr p2 = a, p1 = b;                    // z[j+2], z[j+3]
+  for (uint64_t j = 0; j + 4 < m; j++) {
+    HFr nx = (p2 + small[j % 7 + 1]) * p1;
+    nx.to_bytes(z_out + 32 * (j + 4));
+    p2 = p1;
+    p1 = nx;
+  }
+  (p1 * p2).to_bytes(z_out + 32);        // z[1] = z[m-1] * z[m-2]
   return ZKB_OK;
 }
 
@@ -358,76 +358,103 @@ int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint3
     std::memcpy(w.l, wroot, 32);
     HFr zt = hpow_u64(tau, n) - HFr::one();
     HFr ninv = hpow_u64(HFr::from_u64(2), log_n).inverse();
-    std::vector<HFr> L(n), den(n), pre(n);
-    HFr wj = HFr::one(), scale = zt * ninv;
-    for (uint64_t j = 0; j < n; j++) {
-      den[j] = tau - wj;
-      L[j] = scale * wj;
-      wj = wj * w;
-    }
-    HFr acc = HFr::one();
-    for (uint64_t j = 0; j < n; j++) {
-      pre[j] = acc;
-      acc = acc * den[j];
-    }
-    HFr ia = acc.inverse();
-    for (uint64_t j = n; j-- > 0;) {
-      L[j] = L[j] * (ia * pre[j]);
-      ia = ia * den[j];
-    }
-    std::vector<HFr> u(m, HFr::zero()), v(m, HFr::zero()), wv(m, HFr::zero());
+    // u_i(tau), v_i(tau), w_i(tau) for the variables this key needs: the rank's range [lo, lo+cnt)
+    // and the instance variables 0, 1 (kept in their own slots).  The Lagrange values
+    // L_j = (tau^n - 1)/n * w^j / (tau - w^j) are streamed in blocks (one inversion per block), so
+    // host memory stays O(cnt) whatever the circuit size.
+    const uint64_t lo = pk->qfirst[0], cnt = pk->qcount[0];
+    std::vector<HFr> uvw[3];
+    for (auto& x : uvw) x.assign(cnt, HFr::zero());
+    HFr inst[3][2];
+    for (auto& x : inst) x[0] = x[1] = HFr::zero();
     std::vector<HFr> coeff_m;
     for (uint32_t c : cs.coeff_values) coeff_m.push_back(HFr::from_u64(c));
-    std::vector<HFr>* uvw[3] = {&u, &v, &wv};
-    for (int k = 0; k < 3; k++)
-      for (uint64_t j = 0; j < cs.ncons; j++)
-        for (uint32_t e = cs.row_ptr[k][j]; e < cs.row_ptr[k][j + 1]; e++) {
-          HFr& t = (*uvw[k])[cs.col[k][e]];
-          t = t + coeff_m[cs.cidx[k][e]] * L[j];
+    {
+      const uint64_t kBlock = 1ull << 16;
+      std::vector<HFr> L(kBlock), den(kBlock), pre(kBlock);
+      const HFr scale = zt * ninv;
+      HFr wj = HFr::one();
+      for (uint64_t j0 = 0; j0 < n; j0 += kBlock) {
+        const uint64_t len = n - j0 < kBlock ? n - j0 : kBlock;
+        HFr acc = HFr::one();
+        for (uint64_t t = 0; t < len; t++) {
+          den[t] = tau - wj;
+          L[t] = scale * wj;
+          wj = wj * w;
+          pre[t] = acc;
+          acc = acc * den[t];
         }
-    for (uint64_t i = 0; i < 2; i++) u[i] = u[i] + L[cs.ncons + i];
-    HFr gi = gamma.inverse(), di = delta.inverse();
-    // scalars (canonical) for every query; one reusable staging vector
-    std::vector<uint64_t> sc(4 * n);
-    for (uint64_t i = 0; i < m; i++) canon_into(u[i], sc, i);
-    if ((rc = make_query(ctx, sc, pk->qfirst[0], pk->qcount[0], 0, &pk->a_query))) throw rc;
-    for (uint64_t i = 0; i < m; i++) canon_into(v[i], sc, i);
-    if ((rc = make_query(ctx, sc, pk->qfirst[1], pk->qcount[1], 0, &pk->b_g1_query))) throw rc;
-    if ((rc = make_query(ctx, sc, pk->qfirst[2], pk->qcount[2], 1, &pk->b_g2_query))) throw rc;
-    HFr abc[2];
-    for (uint64_t i = 0; i < m; i++) {
-      HFr t = beta * u[i] + alpha * v[i] + wv[i];
-      // l_query is kept at length m with the instance entries set to the point at infinity
-      // (scalar 0), so that the A / B1 / B2 / L MSMs share one digit extraction and one sort
-      if (i < 2) {
-        abc[i] = t * gi;
-        canon_into(HFr::zero(), sc, i);
-      } else {
-        canon_into(t * di, sc, i);
+        HFr ia = acc.inverse();
+        for (uint64_t t = len; t-- > 0;) {
+          L[t] = L[t] * (ia * pre[t]);
+          ia = ia * den[t];
+        }
+        for (uint64_t t = 0; t < len; t++) {
+          const uint64_t j = j0 + t;
+          if (j < cs.ncons) {
+            for (int k = 0; k < 3; k++)
+              for (uint32_t e2 = cs.row_ptr[k][j]; e2 < cs.row_ptr[k][j + 1]; e2++) {
+                const uint64_t col = cs.col[k][e2];
+                HFr term = coeff_m[cs.cidx[k][e2]] * L[t];
+                if (col < 2) inst[k][col] = inst[k][col] + term;
+                if (col >= lo && col < lo + cnt) uvw[k][col - lo] = uvw[k][col - lo] + term;
+              }
+          } else if (j - cs.ncons < 2) {      // ark-groth16 input-consistency rows of A
+            const uint64_t col = j - cs.ncons;
+            inst[0][col] = inst[0][col] + L[t];
+            if (col >= lo && col < lo + cnt) uvw[0][col - lo] = uvw[0][col - lo] + L[t];
+          }
+        }
       }
     }
-    if ((rc = make_query(ctx, sc, pk->qfirst[3], pk->qcount[3], 0, &pk->l_query))) throw rc;
-    HFr tp = zt * di;
-    for (uint64_t i = 0; i + 1 < n; i++) {
-      canon_into(tp, sc, i);
-      tp = tp * tau;
+    HFr gi = gamma.inverse(), di = delta.inverse();
+    // scalars (canonical) for every query; one reusable staging vector of the shard size
+    uint64_t stage_len = cnt;
+    if (pk->qcount[4] > stage_len) stage_len = pk->qcount[4];
+    if (h_low_bits && (n / world) > stage_len) stage_len = n / world;
+    std::vector<uint64_t> sc(4 * stage_len);
+    for (uint64_t i = 0; i < cnt; i++) canon_into(uvw[0][i], sc, i);
+    if ((rc = make_query(ctx, sc, 0, cnt, 0, &pk->a_query))) throw rc;
+    for (uint64_t i = 0; i < cnt; i++) canon_into(uvw[1][i], sc, i);
+    if ((rc = make_query(ctx, sc, 0, cnt, 0, &pk->b_g1_query))) throw rc;
+    if ((rc = make_query(ctx, sc, 0, cnt, 1, &pk->b_g2_query))) throw rc;
+    HFr abc[2];
+    for (int i = 0; i < 2; i++) abc[i] = (beta * inst[0][i] + alpha * inst[1][i] + inst[2][i]) * gi;
+    for (uint64_t i = 0; i < cnt; i++) {
+      // l_query is kept at length m with the instance entries set to the point at infinity
+      // (scalar 0), so that the A / B1 / B2 / L MSMs share one digit extraction and one sort
+      if (lo + i < 2) canon_into(HFr::zero(), sc, i);
+      else canon_into((beta * uvw[0][i] + alpha * uvw[1][i] + uvw[2][i]) * di, sc, i);
     }
+    if ((rc = make_query(ctx, sc, 0, cnt, 0, &pk->l_query))) throw rc;
+    for (auto& x : uvw) std::vector<HFr>().swap(x);
+    // h_query[k] = tau^k (tau^n - 1) / delta
+    const HFr h0 = zt * di;
     if (h_low_bits) {
-      // h_query in the output layout of the distributed NTT: local [low_loc][high] holds the base
-      // of coefficient (rank*lows + low_loc) + (high << h_low_bits); index n-1 (h has n-1
+      // in the output layout of the distributed NTT: local [low_loc][high] holds the base of
+      // coefficient (rank*lows + low_loc) + (high << h_low_bits); index n-1 (h has n-1
       // coefficients) is the point at infinity
-      canon_into(HFr::zero(), sc, n - 1);
       const uint64_t lows = (1ull << h_low_bits) / world, highs = n >> h_low_bits;
-      std::vector<uint64_t> sel(4 * lows * highs);
-      for (uint64_t lo = 0; lo < lows; lo++)
+      const HFr step = hpow_u64(tau, 1ull << h_low_bits);
+      for (uint64_t l2 = 0; l2 < lows; l2++) {
+        HFr tp = h0 * hpow_u64(tau, rank * lows + l2);
         for (uint64_t hi = 0; hi < highs; hi++) {
-          uint64_t k = (rank * lows + lo) + (hi << h_low_bits);
-          std::memcpy(&sel[4 * (lo * highs + hi)], &sc[4 * k], 32);
+          const uint64_t k = (rank * lows + l2) + (hi << h_low_bits);
+          canon_into(k == n - 1 ? HFr::zero() : tp, sc, l2 * highs + hi);
+          tp = tp * step;
         }
+      }
       pk->qfirst[4] = 0;
       pk->qcount[4] = lows * highs;
-      if ((rc = make_query(ctx, sel, 0, pk->qcount[4], 0, &pk->h_query))) throw rc;
-    } else if ((rc = make_query(ctx, sc, pk->qfirst[4], pk->qcount[4], 0, &pk->h_query))) throw rc;
+    } else {
+      HFr tp = h0 * hpow_u64(tau, pk->qfirst[4]);
+      for (uint64_t i = 0; i < pk->qcount[4]; i++) {
+        canon_into(tp, sc, i);
+        tp = tp * tau;
+      }
+    }
+    if ((rc = make_query(ctx, sc, 0, pk->qcount[4], 0, &pk->h_query))) throw rc;
+    std::vector<uint64_t>().swap(sc);
     if (ctx->pk_precompute) {
       zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
       for (zkb_bases* q : qs)
