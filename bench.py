@@ -359,7 +359,7 @@ def main():
             for i in range(5):
                 barrier()
                 t0 = time.perf_counter()
-                proof = prover.prove(pk, wt.data_ptr(), r, s)
+                proof = prover.prove(pk, wt, r, s)
                 barrier()
                 dt = torch.tensor([time.perf_counter() - t0], device=dev)
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)

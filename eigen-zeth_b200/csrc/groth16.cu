@@ -531,7 +531,7 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     mark(E_START);
     if ((e0 = ctx->msm.flag.ensure(16)) != cudaSuccess) { rc = cuda_fail(ctx, e0, "flag"); break; }
     cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);   // the MSM digit kernels flag a non-canonical witness
-    cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st);
     mark(E_H2D);
     const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
     fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
@@ -631,7 +631,7 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
   cudaStream_t st = ctx->stream;
   ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
   ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyHostToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st));
   const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
   fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
   void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};

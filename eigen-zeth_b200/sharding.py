@@ -98,10 +98,31 @@ class FourStepProver:
     def h_low_bits(self) -> int:
         return self.d1
 
+    def _stage_witness(self, witness):
+        """With several ranks and a (pinned) CPU tensor as witness, every rank uploads only its 1/N
+        slice over PCIe and the slices are all-gathered over NVLink; returns a pointer the library
+        accepts (host or device)."""
+        import torch
+        if isinstance(witness, torch.Tensor):
+            if self.world == 1 or witness.is_cuda:
+                self._keep = witness
+                return witness.data_ptr()
+            import torch.distributed as dist
+            nbytes = witness.numel() * witness.element_size()
+            flat = witness.view(torch.uint8).reshape(-1)
+            per = nbytes // self.world
+            if not hasattr(self, "_wfull") or self._wfull.numel() != nbytes:
+                self._wfull = torch.empty(nbytes, dtype=torch.uint8, device=self.ntt.device)
+            with torch.cuda.stream(self.ntt.stream):
+                own = flat[self.rank * per:(self.rank + 1) * per].to(self.ntt.device, non_blocking=True)
+                dist.all_gather_into_tensor(self._wfull, own)
+            return self._wfull.data_ptr()
+        return witness
+
     def witness_map(self, pk, witness):
         """-> torch tensor with this rank's h coefficients (canonical) in layout d1."""
         ctx, nt, L = self.ctx, self.ntt, self.log_n
-        ptrs = ctx.groth16_witness_dev(pk, witness)
+        ptrs = ctx.groth16_witness_dev(pk, self._stage_witness(witness))
         for p, buf in zip(ptrs, self.bufs):
             ctx.fr_gather_layout_dev(p, buf.data_ptr(), L, self.d0, self.world, self.rank)
         for buf in self.bufs:

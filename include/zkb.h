@@ -159,6 +159,8 @@ int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wit
  * (device, Montgomery, natural order; pointers returned in d_abc_out, owned by the key);
  * (2) ... the caller runs the NTT chain (dist_ntt.py) ...; (3) the five MSMs with h read from d_h
  * (canonical, in the key's local h order) -> this rank's 384-byte partial sums */
+/* `witness` may be a host pointer or a device pointer on the ctx's GPU (e.g. the output of an
+ * NVLink all-gather of per-rank slices, so that each rank uploads only 1/N of it over PCIe) */
 int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, void* d_abc_out[3]);
 int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
                         uint8_t partial_out[ZKB_INTERMEDIATE_BYTES]);

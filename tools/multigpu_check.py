@@ -71,7 +71,8 @@ def main():
     proof4 = prover.prove(fpk, w, r, s)
     dist.barrier()
     t0 = time.perf_counter()
-    proof4b = prover.prove(fpk, w, r, s)
+    wt16 = torch.frombuffer(bytearray(w), dtype=torch.uint8).pin_memory()
+    proof4b = prover.prove(fpk, wt16, r, s)          # witness uploaded in slices + NVLink all-gather
     dist.barrier()
     dt = time.perf_counter() - t0
     if os.environ.get("ZKB_STAGES"):
@@ -83,7 +84,7 @@ def main():
         for i in range(3):
             tm = {}
             dist.barrier()
-            p2.prove(k2, wt.data_ptr(), r, s, timings=tm)
+            p2.prove(k2, wt, r, s, timings=tm)
         if rank == 0:
             print("stages 2^%d world=%d:" % (glog, world), {k: round(v * 1e3, 2) for k, v in tm.items()}, flush=True)
         k2.free()

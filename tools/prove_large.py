@@ -35,7 +35,7 @@ for i in range(reps + 1):
     tm = {} if i == reps else None
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    proof = prover.prove(pk, wt.data_ptr(), r, s, timings=tm)
+    proof = prover.prove(pk, wt, r, s, timings=tm)
     dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
