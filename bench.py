@@ -83,6 +83,32 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def uniform_fr_scalars(n, seed):
+    """n scalars uniform in [0, r) as an (n, 4) uint64 numpy array (little-endian limbs):
+    254-bit draws with rejection, the distribution SURVEY.md 8(d) prescribes."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    limbs = [(R_MOD >> (64 * i)) & (2**64 - 1) for i in range(4)]
+    out = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] &= np.uint64((1 << 62) - 1)
+    while True:
+        ge = np.zeros(n, dtype=bool)          # out >= r, lexicographic from the top limb
+        eq = np.ones(n, dtype=bool)
+        for i in (3, 2, 1, 0):
+            ge |= eq & (out[:, i] > np.uint64(limbs[i]))
+            eq &= out[:, i] == np.uint64(limbs[i])
+        ge |= eq
+        bad = np.nonzero(ge)[0]
+        if bad.size == 0:
+            return out
+        fresh = rng.integers(0, 2**64, size=(bad.size, 4), dtype=np.uint64)
+        fresh[:, 3] &= np.uint64((1 << 62) - 1)
+        out[bad] = fresh
+
+
 def cpu_baseline_msm(sample_log=CPU_SAMPLE_LOG, reps=1):
     """oracle B (arkworks-style VariableBaseMSM restatement) on all host threads; bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -173,10 +199,7 @@ def main():
     if not args.classic:
         # proving-key bases are fixed: expand them once to their window multiples in HBM
         bases.precompute(0)
-    g = torch.Generator(device="cpu").manual_seed(SEED + log_n + 7919 * rank)
-    sc_host = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, generator=g)
-    sc_host[:, 7] &= 0x0FFFFFFF                     # < 2^252 < r: canonical scalars
-    sc_host = sc_host.pin_memory()
+    sc_host = torch.from_numpy(uniform_fr_scalars(n, SEED + log_n + 7919 * rank).view("int64")).pin_memory()
     sc_dev = sc_host.to(dev, non_blocking=False)
     part = torch.zeros(64, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world * 64, dtype=torch.uint8, device=dev)
@@ -282,8 +305,7 @@ def main():
 
     if rank == 0 and not args.no_extras and world == 1:
         # ---- NTT 2^24 (device resident, Montgomery in/out) and Groth16 2^22
-        x = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev)
-        x[:, 7] &= 0x0FFFFFFF
+        x = sc_dev.clone()
         ntt = {}
         for full in (0, 1):
             ctx.set("ntt_full_twiddles", full)

@@ -42,11 +42,8 @@ for log_n in sizes:
     # ---- inputs (same generators as the CPU side)
     scal = ob.random_scalars(n, seed) if log_n <= 22 else None
     if scal is None:
-        g = torch.Generator().manual_seed(seed)
-        sc = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, generator=g)
-        sc[:, 7] &= 0x0FFFFFFF
-        sc_dev = sc.cuda()
-        del sc
+        from bench import uniform_fr_scalars
+        sc_dev = torch.from_numpy(uniform_fr_scalars(n, seed).view("int64")).cuda()
     else:
         sc_dev = torch.frombuffer(bytearray(scal), dtype=torch.uint8).cuda()
     # ---- NTT

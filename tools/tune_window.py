@@ -8,8 +8,9 @@ stream = torch.cuda.ExternalStream(ctx.stream)
 out = {}
 for log_n in (14, 16, 18, 19, 20, 21, 22, 23, 24):
     n = 1 << log_n
-    sc = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda")
-    sc[:, 7] &= 0x0FFFFFFF
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import uniform_fr_scalars
+    sc = torch.from_numpy(uniform_fr_scalars(n, log_n).view("int64")).cuda()
     res = torch.zeros(64, dtype=torch.uint8, device="cuda")
     for c in range(max(8, log_n - 7), min(23, log_n + 1) + 1):
         bases = ctx.synthetic_bases(n, 1)
