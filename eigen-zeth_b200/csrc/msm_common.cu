@@ -84,7 +84,7 @@ int msm_auto_window(uint64_t n, bool precomputed) {
     if (log_n <= 16) return 15;   // 17
     if (log_n <= 19) return 17;   // 15
     if (log_n <= 22) return 20;   // 13
-    return 23;                    // 12
+    return 22;                    // 12
   }
   // classic: one bucket set per window, keep buckets << points
   int c = log_n - 6;
