@@ -7,7 +7,9 @@
 // Appendix B): domain = 2^log_n >= #constraints + #instance, coefficient-form H, coset shift 5.
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstring>
+#include <map>
 #include <new>
 #include <vector>
 
@@ -37,6 +39,7 @@ struct zkb_pk {
   void* d_proof = nullptr;           // 256 B + r,s staging (64 B)
   // point-range shard held by this key: query q covers [qfirst[q], qfirst[q] + qcount[q]) of the
   // full query (q = 0 a, 1 b_g1, 2 b_g2, 3 l, 4 h); world == 1 means the whole key
+  uint32_t n_inst = 2;       // instance variables incl. the constant one: z[0] = 1, z[1..n_inst)
   uint32_t rank = 0, world = 1;
   uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (dist_ntt.py)
   uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
@@ -239,6 +242,31 @@ static int make_query(zkb_ctx* ctx, const std::vector<uint64_t>& scalars_canon, 
   int rc = bases_from_scalars(ctx, ctx->io_a.p, count, is_g2, b->d_pts);
   if (rc) return rc;
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // scalars_canon may die after return
+  return ZKB_OK;
+}
+
+// CSR matrices + coefficient table -> device, and the per-key work buffers
+static int pk_upload_circuit(zkb_ctx* ctx, zkb_pk* pk, const HostR1CS& cs, const std::vector<HFr>& coeff_m) {
+  cudaError_t e;
+  for (int k = 0; k < 3; k++) {
+    if ((e = upload_vec(cs.row_ptr[k], &pk->d_row_ptr[k], ctx->stream)) != cudaSuccess ||
+        (e = upload_vec(cs.col[k], &pk->d_col[k], ctx->stream)) != cudaSuccess ||
+        (e = upload_vec(cs.cidx[k], &pk->d_cidx[k], ctx->stream)) != cudaSuccess)
+      return cuda_fail(ctx, e, "matrix upload");
+  }
+  std::vector<uint32_t> ctab(8 * (coeff_m.size() ? coeff_m.size() : 1));
+  for (size_t i = 0; i < coeff_m.size(); i++) hfr_words(coeff_m[i], &ctab[8 * i]);
+  uint32_t* d_ct = nullptr;
+  if ((e = upload_vec(ctab, &d_ct, ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "coeff upload");
+  pk->d_coeff_table = d_ct;
+  const uint64_t len = pk->n > pk->m ? pk->n : pk->m;
+  void** work[] = {&pk->d_a, &pk->d_b, &pk->d_c, &pk->d_z, &pk->d_zm};
+  for (void** wp : work)
+    if ((e = cudaMalloc(wp, len * 32)) != cudaSuccess) return cuda_fail(ctx, e, "work vectors");
+  if ((e = cudaMalloc(&pk->d_results, ZKB_INTERMEDIATE_BYTES)) != cudaSuccess ||
+      (e = cudaMalloc(&pk->d_proof, ZKB_PROOF_BYTES + 64)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+    return cuda_fail(ctx, e, "result buffers");
   return ZKB_OK;
 }
 
@@ -485,25 +513,133 @@ int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint3
     std::memcpy(vk_out + 192, g2c + 256, 128);
     std::memcpy(vk_out + 320, g2c + 128, 128);
     std::memcpy(vk_out + 448, g1c + 192, 128);
-    // matrices
+    if ((rc = pk_upload_circuit(ctx, pk, cs, coeff_m))) throw rc;
+  } catch (int code) {
+    zkb_pk_free(pk);
+    return code;
+  } catch (const std::bad_alloc&) {
+    zkb_pk_free(pk);
+    return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  }
+  *out = pk;
+  return ZKB_OK;
+}
+
+}  // extern "C" (reopened below)
+
+// external bases (canonical affine bytes) -> device-resident zkb_bases, optionally zero-padded in front
+static int bases_from_bytes(zkb_ctx* ctx, const uint8_t* pts, uint64_t count, uint64_t pad_front, int is_g2,
+                            zkb_bases** out) {
+  const size_t sz = is_g2 ? 128 : 64;
+  for (uint64_t i = 0; i < count * (sz / 32); i++) {
+    uint64_t w[4];
+    std::memcpy(w, pts + 32 * i, 32);
+    if (!host::HFq::lt_mod(w)) return set_error(ctx, ZKB_EINVAL, "non-canonical Fq coordinate in a query");
+  }
+  zkb_bases* b = new (std::nothrow) zkb_bases();
+  if (!b) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  b->device = ctx->device;
+  b->is_g2 = is_g2;
+  b->n = count + pad_front;
+  cudaError_t e = cudaMalloc(&b->d_pts, (b->n ? b->n : 1) * sz);
+  if (e != cudaSuccess) {
+    delete b;
+    return cuda_fail(ctx, e, "query allocation");
+  }
+  *out = b;
+  ZKB_CUDA(ctx, cudaMemsetAsync(b->d_pts, 0, pad_front * sz, ctx->stream));
+  ZKB_CUDA(ctx, cudaMemcpyAsync((char*)b->d_pts + pad_front * sz, pts, count * sz, cudaMemcpyHostToDevice, ctx->stream));
+  if (is_g2) msm_bases_to_mont_g2(b->d_pts, b->n, ctx->stream);
+  else msm_bases_to_mont_g1(b->d_pts, b->n, ctx->stream);
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+extern "C" {
+
+int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
+  if (!ctx) return ZKB_EINVAL;
+  BusyGuard guard(ctx);
+  if (!guard.ok) return ZKB_EBUSY;
+  if (!d || !out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  const uint64_t n = 1ull << d->log_n, m = d->n_vars, n_inst = uint64_t(d->n_public) + 1;
+  if (d->log_n < 1 || d->log_n > 26 || m < n_inst || m >= (1ull << 31) ||
+      d->n_constraints + n_inst > n || n_inst > 64)
+    return set_error(ctx, ZKB_EINVAL, "inconsistent circuit dimensions (domain must hold constraints + instance)");
+  for (int k = 0; k < 3; k++)
+    if (!d->row_ptr[k] || (d->row_ptr[k][d->n_constraints] && (!d->col[k] || !d->coeff[k])))
+      return set_error(ctx, ZKB_EINVAL, "null matrix");
+  if (!d->a_query || !d->b_g1_query || !d->b_g2_query || !d->h_query || (m > n_inst && !d->l_query) ||
+      !d->alpha_g1 || !d->beta_g1 || !d->delta_g1 || !d->beta_g2 || !d->delta_g2)
+    return set_error(ctx, ZKB_EINVAL, "null query");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  zkb_pk* pk = new (std::nothrow) zkb_pk();
+  if (!pk) return set_error(ctx, ZKB_ENOMEM, "out of host memory");
+  int rc = ZKB_OK;
+  try {
+    pk->device = ctx->device;
+    pk->log_n = d->log_n;
+    pk->n = n;
+    pk->m = m;
+    pk->ncons = d->n_constraints;
+    pk->n_inst = uint32_t(n_inst);
+    const uint64_t qlen[5] = {m, m, m, m, n - 1};
+    for (int q = 0; q < 5; q++) pk->qcount[q] = qlen[q];
+    // matrices: validate, de-duplicate coefficients into a table
+    HostR1CS cs;
+    cs.m = m;
+    cs.ncons = d->n_constraints;
+    std::vector<HFr> coeff_m;
+    std::map<std::array<uint64_t, 4>, uint32_t> seen;
     for (int k = 0; k < 3; k++) {
-      if ((e = upload_vec(cs.row_ptr[k], &pk->d_row_ptr[k], ctx->stream)) != cudaSuccess ||
-          (e = upload_vec(cs.col[k], &pk->d_col[k], ctx->stream)) != cudaSuccess ||
-          (e = upload_vec(cs.cidx[k], &pk->d_cidx[k], ctx->stream)) != cudaSuccess)
-        throw cuda_fail(ctx, e, "matrix upload");
+      const uint32_t nnz = d->row_ptr[k][cs.ncons];
+      cs.row_ptr[k].assign(d->row_ptr[k], d->row_ptr[k] + cs.ncons + 1);
+      cs.col[k].assign(d->col[k], d->col[k] + nnz);
+      cs.cidx[k].resize(nnz);
+      if (cs.row_ptr[k][0] != 0) throw set_error(ctx, ZKB_EINVAL, "row_ptr must start at 0");
+      for (uint64_t j = 0; j < cs.ncons; j++)
+        if (cs.row_ptr[k][j] > cs.row_ptr[k][j + 1]) throw set_error(ctx, ZKB_EINVAL, "row_ptr not monotone");
+      for (uint32_t e2 = 0; e2 < nnz; e2++) {
+        if (cs.col[k][e2] >= m) throw set_error(ctx, ZKB_EINVAL, "column index out of range");
+        std::array<uint64_t, 4> key;
+        std::memcpy(key.data(), d->coeff[k] + 32 * uint64_t(e2), 32);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          HFr c;
+          if (!HFr::from_bytes(d->coeff[k] + 32 * uint64_t(e2), &c))
+            throw set_error(ctx, ZKB_EINVAL, "non-canonical matrix coefficient");
+          it = seen.emplace(key, uint32_t(coeff_m.size())).first;
+          coeff_m.push_back(c);
+        }
+        cs.cidx[k][e2] = it->second;
+      }
     }
-    std::vector<uint32_t> ctab(8 * coeff_m.size());
-    for (size_t i = 0; i < coeff_m.size(); i++) hfr_words(coeff_m[i], &ctab[8 * i]);
-    uint32_t* d_ct = nullptr;
-    if ((e = upload_vec(ctab, &d_ct, ctx->stream)) != cudaSuccess) throw cuda_fail(ctx, e, "coeff upload");
-    pk->d_coeff_table = d_ct;
-    void** work[] = {&pk->d_a, &pk->d_b, &pk->d_c, &pk->d_z, &pk->d_zm};
-    for (void** wp : work)
-      if ((e = cudaMalloc(wp, n * 32)) != cudaSuccess) throw cuda_fail(ctx, e, "work vectors");
-    if ((e = cudaMalloc(&pk->d_results, ZKB_INTERMEDIATE_BYTES)) != cudaSuccess ||
-        (e = cudaMalloc(&pk->d_proof, ZKB_PROOF_BYTES + 64)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
-      throw cuda_fail(ctx, e, "result buffers");
+    if ((rc = bases_from_bytes(ctx, d->a_query, m, 0, 0, &pk->a_query))) throw rc;
+    if ((rc = bases_from_bytes(ctx, d->b_g1_query, m, 0, 0, &pk->b_g1_query))) throw rc;
+    if ((rc = bases_from_bytes(ctx, d->b_g2_query, m, 0, 1, &pk->b_g2_query))) throw rc;
+    // l_query arrives without the instance entries (ark-groth16); stored padded, see zkb_pk_query
+    if ((rc = bases_from_bytes(ctx, d->l_query, m - n_inst, n_inst, 0, &pk->l_query))) throw rc;
+    if ((rc = bases_from_bytes(ctx, d->h_query, n - 1, 0, 0, &pk->h_query))) throw rc;
+    if (ctx->pk_precompute) {
+      zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
+      for (zkb_bases* q : qs)
+        if (q->n && (rc = bases_precompute_nolock(ctx, q, 0))) throw rc;
+    }
+    // fixed points -> Montgomery on device: alpha_g1 | beta_g1 | delta_g1 | beta_g2 | delta_g2
+    uint8_t f1[192], f2[256];
+    std::memcpy(f1, d->alpha_g1, 64); std::memcpy(f1 + 64, d->beta_g1, 64); std::memcpy(f1 + 128, d->delta_g1, 64);
+    std::memcpy(f2, d->beta_g2, 128); std::memcpy(f2 + 128, d->delta_g2, 128);
+    zkb_bases *b1 = nullptr, *b2 = nullptr;
+    if ((rc = bases_from_bytes(ctx, f1, 3, 0, 0, &b1))) throw rc;
+    if ((rc = bases_from_bytes(ctx, f2, 2, 0, 1, &b2))) { zkb_bases_free(b1); throw rc; }
+    cudaError_t e = cudaMalloc(&pk->d_fixed, 3 * 64 + 2 * 128);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pk->d_fixed, b1->d_pts, 3 * 64, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((char*)pk->d_fixed + 192, b2->d_pts, 2 * 128, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    zkb_bases_free(b1);
+    zkb_bases_free(b2);
+    if (e != cudaSuccess) throw cuda_fail(ctx, e, "fixed points");
+    if ((rc = pk_upload_circuit(ctx, pk, cs, coeff_m))) throw rc;
   } catch (int code) {
     zkb_pk_free(pk);
     return code;
@@ -539,7 +675,7 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     for (int k = 0; k < 3; k++)
       r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
                                              (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
-                                             (Fr*)outs[k], pk->ncons, n, k == 0, 2);
+                                             (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst);
     mark(E_SPMV);
     CosetTables* ct;
     if ((rc = coset_tables(ctx, pk->log_n, &ct))) break;
@@ -638,7 +774,7 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
   for (int k = 0; k < 3; k++)
     r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
                                            (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
-                                           (Fr*)outs[k], pk->ncons, n, k == 0, 2);
+                                           (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst);
   ctx->launches += 4;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;

@@ -22,7 +22,7 @@ EXPORTS = [
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_bases_precompute", "zkb_bases_window",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
-    "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_free", "zkb_pk_query",
+    "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
     "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
@@ -34,6 +34,14 @@ class ZkbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("zkb error %d: %s" % (code, msg))
         self.code = code
+
+
+class PkDesc(C.Structure):
+    _fields_ = [("log_n", C.c_uint32), ("n_public", C.c_uint32), ("n_vars", C.c_uint64), ("n_constraints", C.c_uint64),
+                ("row_ptr", C.c_void_p * 3), ("col", C.c_void_p * 3), ("coeff", C.c_void_p * 3),
+                ("a_query", C.c_void_p), ("b_g1_query", C.c_void_p), ("b_g2_query", C.c_void_p),
+                ("l_query", C.c_void_p), ("h_query", C.c_void_p), ("alpha_g1", C.c_void_p), ("beta_g1", C.c_void_p),
+                ("delta_g1", C.c_void_p), ("beta_g2", C.c_void_p), ("delta_g2", C.c_void_p)]
 
 
 class ProveTimings(C.Structure):
@@ -92,6 +100,7 @@ def load_library() -> C.CDLL:
     if hasattr(lib, "zkb_pk_synthetic"):
         lib.zkb_pk_synthetic.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
         lib.zkb_pk_synthetic_shard.argtypes = [vp, u32, u64, u32, u32, C.POINTER(vp), vp]
+        lib.zkb_pk_load.argtypes = [vp, C.POINTER(PkDesc), C.POINTER(vp)]
         lib.zkb_pk_synthetic_shard_ex.argtypes = [vp, u32, u64, u32, u32, u32, C.POINTER(vp), vp]
         lib.zkb_groth16_witness_dev.argtypes = [vp, vp, vp, C.POINTER(vp)]
         lib.zkb_groth16_msm_dev.argtypes = [vp, vp, vp, vp]
@@ -320,6 +329,34 @@ class Context:
         vk = C.create_string_buffer(VK_BYTES)
         self._check(self.lib.zkb_pk_synthetic_shard_ex(self.h, log_n, seed, rank, world, h_low_bits, C.byref(h), vk))
         return ProvingKey(self, h, vk.raw, log_n)
+
+    def pk_load(self, log_n: int, n_vars: int, n_public: int, matrices, queries: dict, fixed: dict, vk: bytes = b"") -> ProvingKey:
+        """matrices: three (row_ptr list[int], col list[int], coeff bytes) for A, B, C;
+        queries: a_query, b_g1_query, b_g2_query, l_query, h_query (canonical affine bytes);
+        fixed: alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2."""
+        import array
+        d = PkDesc()
+        d.log_n, d.n_public, d.n_vars = log_n, n_public, n_vars
+        d.n_constraints = len(matrices[0][0]) - 1
+        keep = []
+        for k, (rp, col, coeff) in enumerate(matrices):
+            a_rp, a_col = array.array("I", rp), array.array("I", col)
+            b_co = C.create_string_buffer(bytes(coeff), max(len(coeff), 1))
+            keep += [a_rp, a_col, b_co]
+            d.row_ptr[k] = a_rp.buffer_info()[0]
+            d.col[k] = a_col.buffer_info()[0] if len(a_col) else None
+            d.coeff[k] = C.cast(b_co, C.c_void_p)
+        for name in ("a_query", "b_g1_query", "b_g2_query", "l_query", "h_query"):
+            b = C.create_string_buffer(bytes(queries[name]), max(len(queries[name]), 1))
+            keep.append(b)
+            setattr(d, name, C.cast(b, C.c_void_p))
+        for name in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2"):
+            b = C.create_string_buffer(bytes(fixed[name]), len(fixed[name]))
+            keep.append(b)
+            setattr(d, name, C.cast(b, C.c_void_p))
+        h = C.c_void_p()
+        self._check(self.lib.zkb_pk_load(self.h, C.byref(d), C.byref(h)))
+        return ProvingKey(self, h, vk, log_n)
 
     def groth16_witness_dev(self, pk: ProvingKey, witness):
         """H2D + R1CS products; returns the device pointers of the a, b, c evaluation vectors."""

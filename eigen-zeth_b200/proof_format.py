@@ -97,6 +97,32 @@ def public_input_from_json(json_str: str) -> bytes:
     return x.to_bytes(32, "little")
 
 
+def vk_to_json(vk: bytes) -> str:
+    """576-byte verifying key (include/zkb.h layout) -> the JSON a Groth16Verifier.sol generator
+    takes.  G2 coordinates are written [c0, c1] — the order the contract behind
+    reference contracts/EigenZkVM.json stores them in and the order of
+    `pi_b` in proof.json; its pairing library performs the swap the 0x08 precompile needs."""
+    if len(vk) != 576:
+        raise ValueError("verifying key must be 576 bytes")
+    c = [_le(vk[i:i + 32]) for i in range(0, 576, 32)]
+    if any(v >= Q for v in c):
+        raise ValueError("coordinate not reduced modulo q")
+    g1 = lambda i: [str(c[i]), str(c[i + 1])]
+    g2 = lambda i: [[str(c[i]), str(c[i + 1])], [str(c[i + 2]), str(c[i + 3])]]
+    return json.dumps({"protocol": "groth16", "curve": "BN128", "nPublic": 1, "vk_alpha_1": g1(0), "vk_beta_2": g2(2),
+                       "vk_gamma_2": g2(6), "vk_delta_2": g2(10), "IC": [g1(14), g1(16)]}, indent=1)
+
+
+def vk_from_json(json_str: str) -> bytes:
+    v = json.loads(json_str)
+    flat = list(v["vk_alpha_1"]) + [x for pair in v["vk_beta_2"] for x in pair] + [x for pair in v["vk_gamma_2"] for x in pair] \
+        + [x for pair in v["vk_delta_2"] for x in pair] + [x for pt in v["IC"] for x in pt]
+    vals = [_u256_from_dec_str(x) for x in flat]
+    if len(vals) != 18 or any(x >= Q for x in vals):
+        raise ValueError("malformed verifying key")
+    return b"".join(x.to_bytes(32, "little") for x in vals)
+
+
 @dataclass
 class ProofResult:
     """src/db/mod.rs:63-71; stored under BATCH_PROOF_{n} (src/settlement/worker.rs:179-182)."""

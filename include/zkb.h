@@ -128,6 +128,26 @@ int zkb_pk_synthetic(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
  * this GPU (one process per GPU; the MSM partial sums are combined above this layer) */
 int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,
                            zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]);
+/* An externally generated key (f4 of SURVEY.md 8f: circuits other than the synthetic chain).
+ * Matrices are CSR over the variables z = (1, public..., private...): row_ptr has n_constraints + 1
+ * entries, coeff holds one canonical 32-byte Fr per non-zero.  Queries are the fields of
+ * ark-groth16's ProvingKey as canonical affine bytes (all-zero = infinity): a_query, b_g1_query,
+ * b_g2_query have n_vars points, l_query n_vars - n_public - 1, h_query 2^log_n - 1.  The domain
+ * must satisfy n_constraints + n_public + 1 <= 2^log_n (ark-groth16 appends one input-consistency
+ * row per instance variable).  Everything is copied; the caller's buffers can be freed after. */
+typedef struct zkb_pk_desc {
+  uint32_t log_n;
+  uint32_t n_public;
+  uint64_t n_vars;
+  uint64_t n_constraints;
+  const uint32_t* row_ptr[3];   /* A, B, C */
+  const uint32_t* col[3];
+  const uint8_t* coeff[3];
+  const uint8_t *a_query, *b_g1_query, *b_g2_query, *l_query, *h_query;
+  const uint8_t *alpha_g1, *beta_g1, *delta_g1;   /* 64 B each */
+  const uint8_t *beta_g2, *delta_g2;              /* 128 B each */
+} zkb_pk_desc;
+int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* desc, zkb_pk** out);
 /* as above, with h_query held in the output layout of the four-step NTT: local [low_loc][high]
  * is the base of coefficient (rank * 2^h_low_bits / world + low_loc) + (high << h_low_bits) */
 int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t rank, uint32_t world,

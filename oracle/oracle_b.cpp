@@ -734,6 +734,15 @@ void ob_pk_vk(void* pkv, uint8_t* out) {
   aff_put(pk->gamma_abc[0], out + 448);
   aff_put(pk->gamma_abc[1], out + 512);
 }
+// alpha_g1 | beta_g1 | delta_g1 (192 B) then beta_g2 | delta_g2 (256 B)
+void ob_pk_fixed(void* pkv, uint8_t* out) {
+  ProvingKey* pk = (ProvingKey*)pkv;
+  aff_put(pk->alpha_g1, out);
+  aff_put(pk->beta_g1, out + 64);
+  aff_put(pk->delta_g1, out + 128);
+  aff_put(pk->beta_g2, out + 192);
+  aff_put(pk->delta_g2, out + 320);
+}
 // query export: which = 0 a, 1 b_g1, 2 b_g2, 3 l, 4 h ; returns the number of points
 uint64_t ob_pk_query(void* pkv, int which, uint8_t* out) {
   ProvingKey* pk = (ProvingKey*)pkv;

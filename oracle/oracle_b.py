@@ -46,6 +46,8 @@ def lib():
         l.ob_pk_free.restype = None
         l.ob_pk_vk.argtypes = [vp, vp]
         l.ob_pk_vk.restype = None
+        l.ob_pk_fixed.argtypes = [vp, vp]
+        l.ob_pk_fixed.restype = None
         l.ob_pk_query.argtypes = [vp, C.c_int, vp]
         l.ob_pk_query.restype = u64
         l.ob_synthetic_witness.argtypes = [C.c_uint, C.c_char_p, C.c_char_p, vp]
@@ -113,6 +115,13 @@ class ProvingKey:
         out = C.create_string_buffer(576)
         lib().ob_pk_vk(self.h, out)
         return out.raw
+
+    def fixed(self) -> dict:
+        out = C.create_string_buffer(448)
+        lib().ob_pk_fixed(self.h, out)
+        b = out.raw
+        return {"alpha_g1": b[:64], "beta_g1": b[64:128], "delta_g1": b[128:192], "beta_g2": b[192:320],
+                "delta_g2": b[320:448]}
 
     def query(self, which: int) -> bytes:
         n = lib().ob_pk_query(self.h, which, None)

@@ -128,6 +128,13 @@ def test_proof_format_matches_reference_layout():
         pf.parse_public_input('["12x"]')
     with pytest.raises(ValueError):
         pf.proof_to_json(int(o.Q).to_bytes(32, "little") + bytes(224))
+    # verifying-key export for a Groth16Verifier.sol generator, [c0, c1] order
+    vk = ob.ProvingKey(3, 5).vk()
+    js = pf.vk_to_json(vk)
+    assert pf.vk_from_json(js) == vk
+    doc = json.loads(js)
+    assert doc["vk_beta_2"][0] == [str(int.from_bytes(vk[64:96], "little")), str(int.from_bytes(vk[96:128], "little"))]
+    assert len(doc["IC"]) == 2 and doc["nPublic"] == 1
     pr = pf.ProofResult(7, "p", "i", bytes(range(32)), bytes(32))
     assert pf.ProofResult.from_json(pr.to_json()) == pr
     assert json.loads(pr.to_json())["pre_state_root"] == list(range(32))

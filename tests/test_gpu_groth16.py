@@ -109,3 +109,42 @@ def test_sharded_prove_equals_single_gpu(ctx, zkb, log_n, world):
     assert sums == inter
     assert ctx.groth16_assemble(last, sums, r, s) == want
     assert zkb.groth16_verify(pk.vk, want, wit[32:64])
+
+
+def _csr(rows):
+    rp, col, coeff = [0], [], b""
+    for row in rows:
+        for c_, v in row:
+            col.append(c_)
+            coeff += int(v).to_bytes(32, "little")
+        rp.append(len(col))
+    return rp, col, coeff
+
+
+@pytest.mark.parametrize("log_n", [4, 9, 12])
+def test_pk_load_external_circuit(ctx, zkb, log_n):
+    """zkb_pk_load: R1CS matrices and ark-groth16-style queries produced OUTSIDE the library (here by
+    oracle B) are ingested as bytes; the proof must equal oracle B's, byte for byte."""
+    seed = 0x5EED0004 + 77 + log_n
+    opk = ob.ProvingKey(log_n, seed)
+    cs = o.synthetic_r1cs(log_n)
+    mats = [_csr(cs[k]) for k in ("A", "B", "C")]
+    queries = {n: opk.query(i) for i, n in enumerate(("a_query", "b_g1_query", "b_g2_query", "l_query", "h_query"))}
+    pk = ctx.pk_load(log_n, cs["m"], cs["n_pub"], mats, queries, opk.fixed(), vk=opk.vk())
+    w0, w1, r, s = _inputs(seed)
+    wit = ob.synthetic_witness(log_n, w0, w1)
+    proof, inter, h, _ = ctx.groth16_prove(pk, wit, r, s, want_intermediates=True, want_h=True)
+    oproof, ointer, oh, _ = opk.prove(wit, r, s)
+    assert h == oh and inter == ointer and proof == oproof
+    assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])
+    # error behaviour: inconsistent dimensions / out-of-range column / non-canonical coefficient
+    with pytest.raises(zkb.ZkbError):
+        ctx.pk_load(log_n - 1, cs["m"], cs["n_pub"], mats, queries, opk.fixed())
+    bad = [(mats[0][0], [cs["m"]] + mats[0][1][1:], mats[0][2]), mats[1], mats[2]]
+    with pytest.raises(zkb.ZkbError):
+        ctx.pk_load(log_n, cs["m"], cs["n_pub"], bad, queries, opk.fixed())
+    bad = [(mats[0][0], mats[0][1], int(o.R).to_bytes(32, "little") + mats[0][2][32:]), mats[1], mats[2]]
+    with pytest.raises(zkb.ZkbError):
+        ctx.pk_load(log_n, cs["m"], cs["n_pub"], bad, queries, opk.fixed())
+    pk.free()
+    opk.free()
