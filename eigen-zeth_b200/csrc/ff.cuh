@@ -221,6 +221,161 @@ __device__ __forceinline__ uint32_t sub256(uint32_t (&r)[8], const uint32_t (&a)
   return borrow;
 }
 
+// ---------------------------------------------------------------- squaring
+// a^2 as 16 words: the 28 off-diagonal products a_i a_j (i < j) are laid out in two lanes (odd and
+// even i+j, so every chain walks 64-bit-aligned slots), summed, doubled with funnel shifts, and the
+// 8 diagonal squares are added in one 16-word chain: 36 wide multiplications instead of 64.
+// The schedule is modelled word by word in tools/sqr_model.py.
+__device__ __forceinline__ void square_wide(uint32_t (&t)[16], const uint32_t (&a)[8]) {
+  uint32_t o1, o2, o3, o4, o5, o6, o7, o8, o9, o10, o11, o12, o13, o14;
+  uint32_t e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13;
+  // odd lane, disjoint slots: (0,1)@1 (0,3)@3 (0,5)@5 (0,7)@7 (2,7)@9 (4,7)@11 (6,7)@13
+  asm("mul.lo.u32 %0, %14, %15;\n\t mul.hi.u32 %1, %14, %15;\n\t"
+      "mul.lo.u32 %2, %14, %16;\n\t mul.hi.u32 %3, %14, %16;\n\t"
+      "mul.lo.u32 %4, %14, %17;\n\t mul.hi.u32 %5, %14, %17;\n\t"
+      "mul.lo.u32 %6, %14, %18;\n\t mul.hi.u32 %7, %14, %18;\n\t"
+      "mul.lo.u32 %8, %19, %18;\n\t mul.hi.u32 %9, %19, %18;\n\t"
+      "mul.lo.u32 %10, %20, %18;\n\t mul.hi.u32 %11, %20, %18;\n\t"
+      "mul.lo.u32 %12, %21, %18;\n\t mul.hi.u32 %13, %21, %18;"
+      : "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4), "=&r"(o5), "=&r"(o6), "=&r"(o7), "=&r"(o8),
+        "=&r"(o9), "=&r"(o10), "=&r"(o11), "=&r"(o12), "=&r"(o13), "=&r"(o14)
+      : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(a[2]), "r"(a[4]), "r"(a[6]));
+  // (1,2)@3 (1,4)@5 (1,6)@7 (3,6)@9 (5,6)@11, carry rippled to o14
+  asm("mad.lo.cc.u32 %0, %12, %13, %0;\n\t madc.hi.cc.u32 %1, %12, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %12, %14, %2;\n\t madc.hi.cc.u32 %3, %12, %14, %3;\n\t"
+      "madc.lo.cc.u32 %4, %12, %15, %4;\n\t madc.hi.cc.u32 %5, %12, %15, %5;\n\t"
+      "madc.lo.cc.u32 %6, %16, %15, %6;\n\t madc.hi.cc.u32 %7, %16, %15, %7;\n\t"
+      "madc.lo.cc.u32 %8, %17, %15, %8;\n\t madc.hi.cc.u32 %9, %17, %15, %9;\n\t"
+      "addc.cc.u32 %10, %10, 0;\n\t addc.u32 %11, %11, 0;"
+      : "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7), "+r"(o8), "+r"(o9), "+r"(o10), "+r"(o11),
+        "+r"(o12), "+r"(o13), "+r"(o14)
+      : "r"(a[1]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[3]), "r"(a[5]));
+  // (2,3)@5 (2,5)@7 (4,5)@9
+  asm("mad.lo.cc.u32 %0, %10, %11, %0;\n\t madc.hi.cc.u32 %1, %10, %11, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %12, %2;\n\t madc.hi.cc.u32 %3, %10, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %13, %12, %4;\n\t madc.hi.cc.u32 %5, %13, %12, %5;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.cc.u32 %8, %8, 0;\n\t"
+      "addc.u32 %9, %9, 0;"
+      : "+r"(o5), "+r"(o6), "+r"(o7), "+r"(o8), "+r"(o9), "+r"(o10), "+r"(o11), "+r"(o12), "+r"(o13),
+        "+r"(o14)
+      : "r"(a[2]), "r"(a[3]), "r"(a[5]), "r"(a[4]));
+  // (3,4)@7
+  asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.u32 %7, %7, 0;"
+      : "+r"(o7), "+r"(o8), "+r"(o9), "+r"(o10), "+r"(o11), "+r"(o12), "+r"(o13), "+r"(o14)
+      : "r"(a[3]), "r"(a[4]));
+  // even lane, disjoint slots: (0,2)@2 (0,4)@4 (0,6)@6 (1,7)@8 (3,7)@10 (5,7)@12
+  asm("mul.lo.u32 %0, %12, %13;\n\t mul.hi.u32 %1, %12, %13;\n\t"
+      "mul.lo.u32 %2, %12, %14;\n\t mul.hi.u32 %3, %12, %14;\n\t"
+      "mul.lo.u32 %4, %12, %15;\n\t mul.hi.u32 %5, %12, %15;\n\t"
+      "mul.lo.u32 %6, %16, %17;\n\t mul.hi.u32 %7, %16, %17;\n\t"
+      "mul.lo.u32 %8, %18, %17;\n\t mul.hi.u32 %9, %18, %17;\n\t"
+      "mul.lo.u32 %10, %19, %17;\n\t mul.hi.u32 %11, %19, %17;"
+      : "=&r"(e2), "=&r"(e3), "=&r"(e4), "=&r"(e5), "=&r"(e6), "=&r"(e7), "=&r"(e8), "=&r"(e9),
+        "=&r"(e10), "=&r"(e11), "=&r"(e12), "=&r"(e13)
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[1]), "r"(a[7]), "r"(a[3]), "r"(a[5]));
+  // (1,3)@4 (1,5)@6 (2,6)@8 (4,6)@10
+  asm("mad.lo.cc.u32 %0, %10, %11, %0;\n\t madc.hi.cc.u32 %1, %10, %11, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %12, %2;\n\t madc.hi.cc.u32 %3, %10, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %13, %14, %4;\n\t madc.hi.cc.u32 %5, %13, %14, %5;\n\t"
+      "madc.lo.cc.u32 %6, %15, %14, %6;\n\t madc.hi.cc.u32 %7, %15, %14, %7;\n\t"
+      "addc.cc.u32 %8, %8, 0;\n\t addc.u32 %9, %9, 0;"
+      : "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "+r"(e8), "+r"(e9), "+r"(e10), "+r"(e11), "+r"(e12),
+        "+r"(e13)
+      : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[2]), "r"(a[6]), "r"(a[4]));
+  // (2,4)@6 (3,5)@8
+  asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %11, %2;\n\t madc.hi.cc.u32 %3, %10, %11, %3;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(e6), "+r"(e7), "+r"(e8), "+r"(e9), "+r"(e10), "+r"(e11), "+r"(e12), "+r"(e13)
+      : "r"(a[2]), "r"(a[4]), "r"(a[3]), "r"(a[5]));
+  // S = O + E (into the odd lane, words 2..14)
+  asm("add.cc.u32 %0, %0, %13;\n\t addc.cc.u32 %1, %1, %14;\n\t addc.cc.u32 %2, %2, %15;\n\t"
+      "addc.cc.u32 %3, %3, %16;\n\t addc.cc.u32 %4, %4, %17;\n\t addc.cc.u32 %5, %5, %18;\n\t"
+      "addc.cc.u32 %6, %6, %19;\n\t addc.cc.u32 %7, %7, %20;\n\t addc.cc.u32 %8, %8, %21;\n\t"
+      "addc.cc.u32 %9, %9, %22;\n\t addc.cc.u32 %10, %10, %23;\n\t addc.cc.u32 %11, %11, %24;\n\t"
+      "addc.u32 %12, %12, 0;"
+      : "+r"(o2), "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7), "+r"(o8), "+r"(o9), "+r"(o10),
+        "+r"(o11), "+r"(o12), "+r"(o13), "+r"(o14)
+      : "r"(e2), "r"(e3), "r"(e4), "r"(e5), "r"(e6), "r"(e7), "r"(e8), "r"(e9), "r"(e10), "r"(e11),
+        "r"(e12), "r"(e13));
+  // T = 2 S ...
+  t[1] = o1 << 1;
+  t[2] = __funnelshift_l(o1, o2, 1);
+  t[3] = __funnelshift_l(o2, o3, 1);
+  t[4] = __funnelshift_l(o3, o4, 1);
+  t[5] = __funnelshift_l(o4, o5, 1);
+  t[6] = __funnelshift_l(o5, o6, 1);
+  t[7] = __funnelshift_l(o6, o7, 1);
+  t[8] = __funnelshift_l(o7, o8, 1);
+  t[9] = __funnelshift_l(o8, o9, 1);
+  t[10] = __funnelshift_l(o9, o10, 1);
+  t[11] = __funnelshift_l(o10, o11, 1);
+  t[12] = __funnelshift_l(o11, o12, 1);
+  t[13] = __funnelshift_l(o12, o13, 1);
+  t[14] = __funnelshift_l(o13, o14, 1);
+  t[15] = o14 >> 31;
+  // ... + the diagonal a_i^2 at word 2i, one chain over all 16 words
+  t[0] = a[0] * a[0];
+  asm("mad.hi.cc.u32 %0, %15, %15, %0;\n\t"
+      "madc.lo.cc.u32 %1, %16, %16, %1;\n\t madc.hi.cc.u32 %2, %16, %16, %2;\n\t"
+      "madc.lo.cc.u32 %3, %17, %17, %3;\n\t madc.hi.cc.u32 %4, %17, %17, %4;\n\t"
+      "madc.lo.cc.u32 %5, %18, %18, %5;\n\t madc.hi.cc.u32 %6, %18, %18, %6;\n\t"
+      "madc.lo.cc.u32 %7, %19, %19, %7;\n\t madc.hi.cc.u32 %8, %19, %19, %8;\n\t"
+      "madc.lo.cc.u32 %9, %20, %20, %9;\n\t madc.hi.cc.u32 %10, %20, %20, %10;\n\t"
+      "madc.lo.cc.u32 %11, %21, %21, %11;\n\t madc.hi.cc.u32 %12, %21, %21, %12;\n\t"
+      "madc.lo.cc.u32 %13, %22, %22, %13;\n\t madc.hi.u32 %14, %22, %22, %14;"
+      : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+        "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+}
+
+// a^2 / 2^256 mod p, lazily reduced:  T = a^2 = T_hi 2^256 + T_lo;  U = (T_lo + m p) / 2^256 <= p by
+// eight reduction rounds on the two lanes (the mont_mul schedule without the a*b_i terms);
+// result = T_hi + U < 4p^2/2^256 + p + 1 <= 2p.
+template <class P>
+__device__ __forceinline__ void mont_sqr(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+  uint32_t t[16];
+  square_wide(t, a);
+  uint32_t e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { e[i] = t[i]; o[i] = 0; }
+  redc_step<P>(e, o);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    {
+      uint32_t m = (o[0] + e[1]) * P::M0;
+      lane_shift_mad(o[0], e, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+      lane_mad_spill(o, e[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+    }
+    if (i + 1 < 8) {
+      uint32_t m = (e[0] + o[1]) * P::M0;
+      lane_shift_mad(e[0], o, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+      lane_mad_spill(e, o[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+    }
+  }
+  // U = e + (o >> 32), then r = U + T_hi
+  uint32_t u[8];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=&r"(u[0]), "=&r"(u[1]), "=&r"(u[2]), "=&r"(u[3]), "=&r"(u[4]), "=&r"(u[5]), "=&r"(u[6]),
+        "=&r"(u[7])
+      : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+        "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+  uint32_t hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) hi[i] = t[8 + i];
+  add256(r, u, hi);
+}
+
 // ---------------------------------------------------------------- the field type
 template <class P>
 struct Fp {
@@ -327,7 +482,11 @@ struct Fp {
     mont_mul<P>(r.v, a.v, b.v);
     return r;
   }
-  __device__ __forceinline__ Fp sqr() const { return (*this) * (*this); }
+  __device__ __forceinline__ Fp sqr() const {
+    Fp r;
+    mont_sqr<P>(r.v, v);
+    return r;
+  }
   __device__ __forceinline__ Fp dbl() const { return (*this) + (*this); }
   __device__ __forceinline__ Fp neg() const { return zero() - (*this); }
 
