@@ -482,7 +482,11 @@ struct Fp {
     mont_mul<P>(r.v, a.v, b.v);
     return r;
   }
-  __device__ __forceinline__ Fp sqr() const {
+  // The hot kernels square with the general multiplier: the dedicated squaring below needs 19 %
+  // fewer IMAD.WIDE but its carry ripples, funnel shifts and extra live registers cancel the gain
+  // at the 128-register cap of the MSM walk (measured on B200: 33.65 ms vs 33.1 ms at 2^24).
+  __device__ __forceinline__ Fp sqr() const { return (*this) * (*this); }
+  __device__ __forceinline__ Fp sqr_dedicated() const {
     Fp r;
     mont_sqr<P>(r.v, v);
     return r;

@@ -7,7 +7,8 @@ from helpers import fr_bytes, fr_list, g1_bytes, g1_list, g2_bytes, g2_list, ran
 pytestmark = pytest.mark.gpu
 
 OPS = {0: lambda a, b, p: (a + b) % p, 1: lambda a, b, p: (a - b) % p, 2: lambda a, b, p: a * b % p,
-       3: lambda a, b, p: a * a % p, 4: lambda a, b, p: pow(a, p - 2, p), 5: lambda a, b, p: (-a) % p}
+       3: lambda a, b, p: a * a % p, 4: lambda a, b, p: pow(a, p - 2, p), 5: lambda a, b, p: (-a) % p,
+       6: lambda a, b, p: a * a % p}
 
 
 @pytest.mark.parametrize("field", [0, 1])
