@@ -58,9 +58,17 @@ __global__ void fr_to_mont_copy_kernel(const Fr* in, Fr* out, uint64_t n) {
 __global__ void r1cs_spmv_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
                                  const uint32_t* __restrict__ cidx, const Fr* __restrict__ coeffs,
                                  const Fr* __restrict__ z, Fr* __restrict__ out, uint64_t nrows,
-                                 uint64_t n, int copy_instance, uint32_t n_instance) {
-  uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  if (j >= n) return;
+                                 uint64_t n, int copy_instance, uint32_t n_instance,
+                                 uint32_t log_n, uint32_t low_bits, uint32_t lows, uint32_t low0) {
+  uint64_t pos = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (pos >= n) return;
+  // low_bits == 0: out[j] for every row j < n.  Otherwise only this rank's block of "layout d"
+  // (dist_ntt.py): out[low_loc * H + high] = row (low0 + low_loc) + (high << low_bits), n = lows * H.
+  uint64_t j = pos;
+  if (low_bits) {
+    const uint32_t hbits = log_n - low_bits;
+    j = (low0 + (pos >> hbits)) + ((pos & ((1ull << hbits) - 1)) << low_bits);
+  }
   Fr acc = Fr::zero();
   if (j < nrows) {
     uint32_t lo = row_ptr[j], hi = row_ptr[j + 1];
@@ -72,7 +80,7 @@ __global__ void r1cs_spmv_kernel(const uint32_t* __restrict__ row_ptr, const uin
   } else if (copy_instance && j - nrows < n_instance) {
     acc = Fr::load_nc(z + (j - nrows));   // ark-groth16 input-consistency rows of A
   }
-  acc.store(out + j);
+  acc.store(out + pos);
 }
 
 // a[i] = a[i] * b[i] - c[i]    (the 1/Z(g) factor is folded into the last coset-iNTT table)
@@ -675,7 +683,7 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     for (int k = 0; k < 3; k++)
       r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
                                              (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
-                                             (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst);
+                                             (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst, pk->log_n, 0, 0, 0);
     mark(E_SPMV);
     CosetTables* ct;
     if ((rc = coset_tables(ctx, pk->log_n, &ct))) break;
@@ -762,19 +770,30 @@ static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[
 }
 
 // witness -> a, b, c evaluation vectors (Montgomery, natural order) in pk->d_a / d_b / d_c
-static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness) {
+static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
+                               uint32_t low_bits = 0, uint32_t world = 1, uint32_t rank = 0,
+                               void* const* d_out_opt = nullptr) {
   const uint64_t n = pk->n, m = pk->m;
   cudaStream_t st = ctx->stream;
   ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
   ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st));
   ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st));
-  const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
+  const uint32_t bl_m = uint32_t((m + 255) / 256);
   fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
   void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
+  uint64_t count = n;
+  uint32_t lows = 0;
+  if (low_bits) {
+    lows = (1u << low_bits) / world;
+    count = uint64_t(lows) << (pk->log_n - low_bits);
+    for (int k = 0; k < 3; k++) outs[k] = d_out_opt[k];
+  }
+  const uint32_t bl = uint32_t((count + 255) / 256);
   for (int k = 0; k < 3; k++)
-    r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
-                                           (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
-                                           (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst);
+    r1cs_spmv_kernel<<<bl, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
+                                         (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
+                                         (Fr*)outs[k], pk->ncons, count, k == 0, pk->n_inst, pk->log_n,
+                                         low_bits, lows, rank * lows);
   ctx->launches += 4;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
@@ -844,6 +863,16 @@ int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witne
   d_abc_out[1] = pk->d_b;
   d_abc_out[2] = pk->d_c;
   return rc;
+}
+
+int zkb_groth16_witness_layout_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, uint32_t low_bits,
+                                   uint32_t world, uint32_t rank, void* const d_abc_local[3]) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!witness || !d_abc_local || !d_abc_local[0] || !d_abc_local[1] || !d_abc_local[2])
+    return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (low_bits == 0 || low_bits >= pk->log_n || world == 0 || rank >= world || ((1u << low_bits) % world))
+    return set_error(ctx, ZKB_EINVAL, "bad layout argument");
+  return prove_witness_phase(ctx, pk, witness, low_bits, world, rank, d_abc_local);
 }
 
 int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,

@@ -24,7 +24,7 @@ EXPORTS = [
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
-    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
         lib.zkb_pk_synthetic_shard_ex.argtypes = [vp, u32, u64, u32, u32, u32, C.POINTER(vp), vp]
         lib.zkb_groth16_witness_dev.argtypes = [vp, vp, vp, C.POINTER(vp)]
         lib.zkb_groth16_msm_dev.argtypes = [vp, vp, vp, vp]
+        lib.zkb_groth16_witness_layout_dev.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(vp)]
         lib.zkb_fr_gather_layout_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32]
         lib.zkb_groth16_prove_partial.argtypes = [vp, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_assemble.argtypes = [vp, vp, u8p, u8p, u8p, vp]
@@ -368,6 +369,16 @@ class Context:
             wptr = C.c_void_p(int(witness))
         self._check(self.lib.zkb_groth16_witness_dev(self.h, pk.handle, wptr, ptrs))
         return [int(p) for p in ptrs]
+
+    def groth16_witness_layout_dev(self, pk: ProvingKey, witness, low_bits: int, world: int, rank: int, d_abc):
+        """R1CS products for this rank's layout-d rows only, written into the three given buffers."""
+        ptrs = (C.c_void_p * 3)(*[int(p) for p in d_abc])
+        if isinstance(witness, (bytes, bytearray)):
+            wbuf = C.create_string_buffer(bytes(witness), len(witness))
+            wptr = C.cast(wbuf, C.c_void_p)
+        else:
+            wptr = C.c_void_p(int(witness))
+        self._check(self.lib.zkb_groth16_witness_layout_dev(self.h, pk.handle, wptr, low_bits, world, rank, ptrs))
 
     def groth16_msm_dev(self, pk: ProvingKey, d_h: int) -> bytes:
         out = C.create_string_buffer(INTERMEDIATE_BYTES)

@@ -122,9 +122,8 @@ class FourStepProver:
     def witness_map(self, pk, witness):
         """-> torch tensor with this rank's h coefficients (canonical) in layout d1."""
         ctx, nt, L = self.ctx, self.ntt, self.log_n
-        ptrs = ctx.groth16_witness_dev(pk, self._stage_witness(witness))
-        for p, buf in zip(ptrs, self.bufs):
-            ctx.fr_gather_layout_dev(p, buf.data_ptr(), L, self.d0, self.world, self.rank)
+        ctx.groth16_witness_layout_dev(pk, self._stage_witness(witness), self.d0, self.world, self.rank,
+                                       [b.data_ptr() for b in self.bufs])
         for buf in self.bufs:
             nt.transform(buf, self.d0, inverse=True, post=self.t_coset)      # coefficients * g^k
         for buf in self.bufs:

@@ -182,6 +182,11 @@ int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wit
 /* `witness` may be a host pointer or a device pointer on the ctx's GPU (e.g. the output of an
  * NVLink all-gather of per-rank slices, so that each rank uploads only 1/N of it over PCIe) */
 int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, void* d_abc_out[3]);
+/* as zkb_groth16_witness_dev, but every rank computes only the rows of its "layout d" block and
+ * writes them straight into its own buffers (n / world elements each): the R1CS products are
+ * sharded too */
+int zkb_groth16_witness_layout_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, uint32_t low_bits,
+                                   uint32_t world, uint32_t rank, void* const d_abc_local[3]);
 int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
                         uint8_t partial_out[ZKB_INTERMEDIATE_BYTES]);
 int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
