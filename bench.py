@@ -189,6 +189,14 @@ def main():
     log_n = args.log_n
     n = 1 << log_n
 
+    def on_torch_stream(fn):
+        """collectives run on torch's own stream, ordered against the library stream with events
+        (the library stream is never made torch's current stream)"""
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(stream.record_event())
+        fn()
+        stream.wait_event(cur.record_event())
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -208,16 +216,14 @@ def main():
     def step_device():
         ctx.msm_dev(bases, sc_dev.data_ptr(), n, part.data_ptr())
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, part)
+            on_torch_stream(lambda: dist.all_gather_into_tensor(gathered, part))
             ctx.point_sum_dev(gathered.data_ptr(), world, total.data_ptr())
 
     def step_e2e():
         res = ctx.msm_raw(bases, sc_host.data_ptr(), n)       # H2D + MSM + D2H inside the C ABI
         if world > 1:
             part.copy_(torch.frombuffer(bytearray(res), dtype=torch.uint8))
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, part)
+            on_torch_stream(lambda: dist.all_gather_into_tensor(gathered, part))
             ctx.point_sum_dev(gathered.data_ptr(), world, total.data_ptr())
             ctx.sync()
             res = bytes(total.cpu().numpy())

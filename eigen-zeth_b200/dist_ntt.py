@@ -80,6 +80,17 @@ class FourStepNtt:
             self._tables[key] = t
         return self._tables[key]
 
+    def run_on_torch_stream(self, fn):
+        """Run `fn` (a collective / torch copy) on torch's own current stream, ordered after the work
+        already queued on the library stream and before whatever the library queues next.  The
+        library stream is never made torch's *current* stream: the caching allocator and NCCL's
+        record_stream bookkeeping then only ever see streams torch owns."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.stream.record_event())
+        out = fn()
+        self.stream.wait_event(cur.record_event())
+        return out
+
     # ---- one transform: layout d -> layout L - d
     def phase1(self, x: torch.Tensor, d: int, inverse: bool = False, pre: Optional[torch.Tensor] = None) -> torch.Tensor:
         """steps (a)-(b): returns the packed send buffer [G][Mloc][N1loc]."""
@@ -116,8 +127,7 @@ class FourStepNtt:
             return self.phase2(send, x, d, inverse, post)
         import torch.distributed as dist
         recv = self._tmp[0]                      # phase1 left the packed data in _tmp[1]
-        with torch.cuda.stream(self.stream):
-            dist.all_to_all_single(recv, send)
+        self.run_on_torch_stream(lambda: dist.all_to_all_single(recv, send))
         return self.phase2(recv, x, d, inverse, post)
 
     # ---- helpers for tests / callers that start from a replicated natural-order vector

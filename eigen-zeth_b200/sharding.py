@@ -111,15 +111,14 @@ class FourStepProver:
             nbytes = witness.numel() * witness.element_size()
             flat = witness.view(torch.uint8).reshape(-1)
             per = nbytes // self.world
-            # buffers are allocated on torch's own stream (never under the library's external
-            # stream: the caching allocator would tie the blocks to a stream it does not own)
             if not hasattr(self, "_wfull") or self._wfull.numel() != nbytes:
                 self._wfull = torch.empty(nbytes, dtype=torch.uint8, device=self.ntt.device)
                 self._wown = torch.empty(per, dtype=torch.uint8, device=self.ntt.device)
                 torch.cuda.current_stream(self.ntt.device).synchronize()
-            with torch.cuda.stream(self.ntt.stream):
+            def stage():
                 self._wown.copy_(flat[self.rank * per:(self.rank + 1) * per], non_blocking=True)
                 dist.all_gather_into_tensor(self._wfull, self._wown)
+            self.ntt.run_on_torch_stream(stage)
             return self._wfull.data_ptr()
         return witness
 
