@@ -415,13 +415,22 @@ int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_
     ZKB_CUDA(ctx, cudaMemsetAsync(d_out_affine, 0, aff, ctx->stream));
     return ZKB_OK;
   }
-  uint32_t chunks = ctx->msm_host_chunks > 0 ? uint32_t(ctx->msm_host_chunks) : (n >= (1ull << 20) ? 4 : 1);
+  uint32_t chunks = ctx->msm_host_chunks > 0 ? uint32_t(ctx->msm_host_chunks) : (n >= (1ull << 20) ? 3 : 1);
   if (chunks > 16) chunks = 16;
+  // chunk sizes grow geometrically (1 : 2 : 4 ...): only the first, small upload is exposed, every
+  // later upload hides behind the compute of the chunks before it
+  uint64_t bound[17];
+  bound[0] = 0;
+  for (uint32_t k = 1; k <= chunks; k++) {
+    const uint64_t num = (1ull << k) - 1, den = (1ull << chunks) - 1;
+    bound[k] = k == chunks ? n : (n / den) * num;
+  }
   // one window width for the whole MSM so that every chunk fills the same bucket array
   const uint64_t stride = b->precomp_c ? b->n : 0;
   MsmPlan whole = b->precomp_c ? msm_make_plan(n, b->is_g2, b->precomp_c, ctx->sm_count, stride)
                                : msm_make_plan(n, b->is_g2, int(ctx->msm_window), ctx->sm_count);
-  const uint64_t per = (n + chunks - 1) / chunks;
+  uint64_t per = 0;     // the largest chunk sizes the scratch buffers
+  for (uint32_t k = 0; k < chunks; k++) per = bound[k + 1] - bound[k] > per ? bound[k + 1] - bound[k] : per;
   MsmPlan p = msm_make_plan(per, b->is_g2, whole.c, ctx->sm_count, stride);
   MsmBuffers buf;
   if ((rc = ensure_msm_buffers(ctx, p, &buf, chunks > 1))) return rc;
@@ -435,24 +444,26 @@ int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_
   ZKB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
   ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
   for (uint32_t k = 0; k < chunks; k++) {
-    uint64_t off = uint64_t(k) * per;
-    if (off >= n) { chunks = k; break; }
-    uint64_t cnt = n - off < per ? n - off : per;
-    ZKB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->io_a.p + off * 32, h_scalars + off * 32, cnt * 32,
+    const uint64_t off = bound[k], cnt = bound[k + 1] - bound[k];
+    if (cnt)
+      ZKB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->io_a.p + off * 32, h_scalars + off * 32, cnt * 32,
                                   cudaMemcpyHostToDevice, ctx->copy_stream));
     ZKB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
   }
+  bool first_done = false;
   for (uint32_t k = 0; k < chunks; k++) {
-    uint64_t off = uint64_t(k) * per;
-    uint64_t cnt = n - off < per ? n - off : per;
+    const uint64_t off = bound[k], cnt = bound[k + 1] - bound[k];
+    if (!cnt) continue;
     MsmPlan pk = cnt == per ? p : msm_make_plan(cnt, b->is_g2, whole.c, ctx->sm_count, stride);
     pk.sort_temp_bytes = p.sort_temp_bytes;
     ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
     msm_digits_and_sort(pk, buf, (char*)ctx->io_a.p + off * 32, cnt, uint32_t(first + off), ctx->stream);
-    void* target = k == 0 ? buf.buckets : buf.buckets2;
+    void* target = !first_done ? buf.buckets : buf.buckets2;
     if (b->is_g2) msm_accumulate_g2(pk, buf, b->d_pts, target, ctx->stream);
     else msm_accumulate_g1(pk, buf, b->d_pts, target, ctx->stream);
-    if (k) {
+    const bool merge = first_done;
+    first_done = true;
+    if (merge) {
       if (b->is_g2) msm_merge_g2(pk, buf.buckets, buf.buckets2, ctx->stream);
       else msm_merge_g1(pk, buf.buckets, buf.buckets2, ctx->stream);
     }
