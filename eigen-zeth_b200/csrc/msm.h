@@ -47,6 +47,9 @@ struct MsmBuffers {
 // (c_override is then the width they were built for) and all windows share one bucket set.
 MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint64_t precomp_stride = 0);
 int msm_auto_window(uint64_t n, bool precomputed);
+// resident threads per SM the level-1 walk kernel of each curve is compiled for (launch bounds)
+uint32_t msm_l1_threads_per_sm_g1();
+uint32_t msm_l1_threads_per_sm_g2();
 // out[w * n + i] = 2^{c w} * in[i], w < nwin (affine Montgomery in and out; in may alias out[0..n))
 void msm_precompute_g1(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);
 void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);

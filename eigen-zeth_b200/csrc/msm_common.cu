@@ -106,7 +106,7 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
   p.key_bits = 1;
   while ((1ull << p.key_bits) <= p.n_buckets) p.key_bits++;   // sentinel == n_buckets must fit
   // level-1 threads: one resident wave, never less than 8 entries per thread
-  uint32_t per_sm = is_g2 ? 256 : 512;   // = L1Cfg<F>::kMinBlocks * 128 (msm_impl.cuh)
+  uint32_t per_sm = is_g2 ? msm_l1_threads_per_sm_g2() : msm_l1_threads_per_sm_g1();
   uint64_t t1 = uint64_t(sm_count) * per_sm;
   uint64_t cap = (p.m + 7) / 8;
   if (cap < 1) cap = 1;

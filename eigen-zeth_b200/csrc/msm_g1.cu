@@ -17,4 +17,5 @@ void msm_sum_affine_g1(const void* d_pts, uint32_t n, void* d_out, cudaStream_t 
 void msm_precompute_g1(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s) {
   msm_precompute_t<Fq>(d_in, d_out, n, nwin, c, s);
 }
+uint32_t msm_l1_threads_per_sm_g1() { return 128u * L1Cfg<Fq>::kMinBlocks; }
 }  // namespace zkb
