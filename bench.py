@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 LOG_N = 24
 SEED = 0x5EED0000
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of msm_accumulate_l1_kernel<Fq> at the
+# default workload (2^24 points, c = 22, uniform scalars), from the `ncu --set full` capture
+# summarised in profiles/r01_SUMMARY.md (profiles/r01_ncu_full_msm_accumulate_l1_final_raw.csv)
+L1_TRAFFIC_BYTES_NCU = None
 CPU_SAMPLE_LOG = 20
 
 
@@ -285,14 +289,19 @@ def main():
     roofline = {
         "bound": "int_pipe", "kernel": "msm_accumulate_l1_kernel<Fq>", "achieved": achieved / 1e12,
         "peak": pipe["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE.U32/s",
-        "frac": achieved / pipe["imad_wide_per_s"], "traffic": None,
+        "frac": achieved / pipe["imad_wide_per_s"],
+        "traffic": L1_TRAFFIC_BYTES_NCU if (log_n == LOG_N and bases.window == 22) else None,
         "peak_source": "measured live by zkb_bench_int_pipe (IMAD.WIDE.U32 carry chains); MEASURED_PEAKS.json has no integer-pipe peak",
         "algorithmic_ops_per_launch": imads, "window_bits": c, "windows": nwin,
         "kernel_ms": stage["accumulate_l1"], "stage_ms": stage,
         "whole_msm_frac": imads / (ms_total / args.steps * 1e-3) / pipe["imad_wide_per_s"],
-        "hbm_view": {"algorithmic_bytes": n * nwin * (64 + 8), "achieved_GBps": n * nwin * 72 / (stage["accumulate_l1"] * 1e-3) / 1e9,
-                     "peak_GBps": hbm_peak, "peak_source": hbm_src},
     }
+    # the same kernel against the HBM roofline of MEASURED_PEAKS.json (72 algorithmic bytes per mixed
+    # addition: one 64-byte point gather + key + value): it is nowhere near memory-bound
+    hbm_ach = n * nwin * 72 / (stage["accumulate_l1"] * 1e-3) / 1e9
+    roofline_hbm = {"bound": "hbm", "kernel": "msm_accumulate_l1_kernel<Fq>", "achieved": hbm_ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": hbm_ach / hbm_peak, "traffic": roofline["traffic"],
+                    "algorithmic_bytes_per_launch": n * nwin * 72, "peak_source": hbm_src}
 
     line = {
         "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
@@ -306,7 +315,7 @@ def main():
                    "timing": "CUDA events on the library stream, max over ranks"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 64},
-        "roofline": roofline, "wall_s": wall,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "wall_s": wall,
     }
 
     if rank == 0 and not args.no_extras and world == 1:
