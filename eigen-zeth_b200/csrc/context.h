@@ -41,7 +41,7 @@ struct NttDomain {          // everything that depends on (log_n, direction)
   std::vector<uint32_t> ks; // pass widths
   DevBuf tw_lo, tw_hi, tw_hi_ninv;
   uint32_t lo_bits = 0;
-  std::vector<DevBuf> full; // optional full tables, one per column pass (last one folds 1/n? no: pass 0)
+  std::vector<DevBuf> full; // full inter-pass twiddle tables, one per column pass (1/n folded into pass 0 of an inverse)
   bool full_ready = false;
 };
 

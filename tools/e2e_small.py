@@ -1,5 +1,5 @@
-"""small end-to-end pass over every kernel family, meant to run under compute-sanitizer (one tool per
-gpurun call): NTT (1, 2 and 3 passes, all variants), batched NTT + permute, G1/G2 MSM (classic,
+"""small end-to-end pass over every kernel family (quick health check; written for a
+compute-sanitizer memcheck run, but that tool is closed on this pool): NTT (1, 2 and 3 passes, all variants), batched NTT + permute, G1/G2 MSM (classic,
 precomputed, chunked host path), Groth16 prove 2^8 + pairing check."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,4 +28,4 @@ pk = ctx.pk_synthetic(8, 5)
 w = z.synthetic_witness(8, (3).to_bytes(32, "little"), (4).to_bytes(32, "little"))
 proof, _, _, _ = ctx.groth16_prove(pk, w, (1).to_bytes(32, "little"), (2).to_bytes(32, "little"))
 assert z.groth16_verify(pk.vk, proof, w[32:64])
-print("SANITIZE-SCRIPT OK")
+print("E2E-SMALL OK")
