@@ -29,10 +29,9 @@ namespace zkb {
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 
 // resident CTAs (of 128 threads) per SM for the level-1 walk: 4 x 128 threads at <= 128 registers
-// for G1 (accumulator in registers); 3 x 128 at <= 168 registers for G2, whose accumulator and
-// prefetched points live in shared memory (section 3b)
-template <class F> struct L1Cfg { static constexpr int kMinBlocks = 4; static constexpr bool kSmemWalk = false; };
-template <> struct L1Cfg<Fq2> { static constexpr int kMinBlocks = 3; static constexpr bool kSmemWalk = true; };
+// for G1; the Fq2 accumulator needs the full 255 registers, so 2 x 128 for G2
+template <class F> struct L1Cfg { static constexpr int kMinBlocks = 4; };
+template <> struct L1Cfg<Fq2> { static constexpr int kMinBlocks = 2; };
 
 // ---------------------------------------------------------------- 3. accumulate, level 1
 template <class F>
@@ -86,151 +85,6 @@ __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_k
   } else {
     part_keys[2 * tid + 1] = cur;
     acc.store(part_pts + 2 * tid + 1);
-  }
-}
-
-// ---------------------------------------------------------------- 3b. level 1 with accumulator and points in shared memory
-// The G2 accumulator alone is 64 registers (4 x Fq2); with the point, the prefetched next point
-// and the Fq2 temporaries the register-resident walk needs 255 registers and still spills, so
-// only 8 warps fit an SM and the IMAD.WIDE pipe idles 37 % of the time.  Here the XYZZ
-// accumulator lives in shared memory and the next point is prefetched straight into shared memory
-// with cp.async (no registers held across the gather latency); fields are read just before the
-// multiplication that needs them.  Layout is chunk-major: 16-byte chunk c of thread t at [c][t],
-// so a warp's LDS.128 / STS.128 / LDGSTS.128 is one contiguous 512-byte row.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <class F>
-struct SmemWalk {
-  static constexpr int kChunks = int(sizeof(F) / 16);         // 16-byte chunks per field element
-  static constexpr int kAccChunks = 4 * kChunks;              // x, y, zz, zzz
-  static constexpr int kPtChunks = 2 * kChunks;               // x, y of one affine point
-  static constexpr int kChunksPerThread = kAccChunks + 2 * kPtChunks;   // + two point slots
-  uint4* acc;      // chunk 0 of this thread's accumulator
-  uint4* pts;      // chunk 0 of this thread's point slot 0
-  int stride;      // threads per CTA
-
-  __device__ __forceinline__ static F from_chunks(const uint4* p, int stride) {
-    uint4 q[kChunks];
-#pragma unroll
-    for (int c = 0; c < kChunks; c++) q[c] = p[c * stride];
-    F f;
-    memcpy(&f, q, sizeof(F));
-    return f;
-  }
-  __device__ __forceinline__ F get(int field) const { return from_chunks(acc + field * kChunks * stride, stride); }
-  __device__ __forceinline__ void set(int field, const F& f) const {
-    uint4 q[kChunks];
-    memcpy(q, &f, sizeof(F));
-#pragma unroll
-    for (int c = 0; c < kChunks; c++) acc[(field * kChunks + c) * stride] = q[c];
-  }
-  __device__ __forceinline__ F pt_coord(int slot, int coord) const {
-    return from_chunks(pts + (slot * kPtChunks + coord * kChunks) * stride, stride);
-  }
-  __device__ __forceinline__ void prefetch(int slot, const Affine<F>* g) const {
-    const uint4* src = reinterpret_cast<const uint4*>(g);
-#pragma unroll
-    for (int c = 0; c < kPtChunks; c++) cp_async16(pts + (slot * kPtChunks + c) * stride, src + c);
-    cp_async_commit();
-  }
-  __device__ __forceinline__ XYZZ<F> load_all() const { return {get(0), get(1), get(2), get(3)}; }
-  __device__ __forceinline__ void store_all(const XYZZ<F>& a) const {
-    set(0, a.x); set(1, a.y); set(2, a.zz); set(3, a.zzz);
-  }
-  // acc += (+/-) point in `slot`  (mixed addition, madd-2008-s); `empty` tracks infinity
-  __device__ __forceinline__ void madd(bool& empty, int slot, bool negate) const {
-    F px = pt_coord(slot, 0);
-    F py = pt_coord(slot, 1);
-    if (px.raw_is_zero() && py.raw_is_zero()) return;          // base at infinity
-    if (negate) py = py.neg();
-    if (empty) {
-      set(0, px); set(1, py); set(2, F::one()); set(3, F::one());
-      empty = false;
-      return;
-    }
-    F pp = px * get(2) - get(0);
-    F r = py * get(3) - get(1);
-    if (pp.is_zero()) {               // doubling / cancellation: rare, take the register path
-      XYZZ<F> a = load_all();
-      a.madd(Affine<F>{pt_coord(slot, 0), py});
-      empty = a.is_inf();
-      store_all(a);
-      return;
-    }
-    F p2 = pp.sqr();
-    F p3 = pp * p2;
-    set(2, get(2) * p2);
-    set(3, get(3) * p3);
-    F q = get(0) * p2;
-    F x3 = r.sqr() - p3 - q.dbl();
-    set(0, x3);
-    set(1, r * (q - x3) - get(1) * p3);
-  }
-};
-
-template <class F>
-__global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_smem_kernel(
-    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-    const uint64_t* __restrict__ m_valid_ptr, const Affine<F>* __restrict__ bases,
-    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
-    XYZZ<F>* __restrict__ part_pts, uint32_t n_threads) {
-  extern __shared__ uint4 walk_smem[];
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n_threads) return;
-  const uint64_t m_valid = *m_valid_ptr;
-  const uint64_t len = (m_valid + n_threads - 1) / n_threads;
-  uint64_t start = uint64_t(tid) * len;
-  uint64_t end = start + len < m_valid ? start + len : m_valid;
-  if (start >= end) {
-    part_keys[2 * tid] = kInvalidKey;
-    part_keys[2 * tid + 1] = kInvalidKey;
-    return;
-  }
-  const int nthr = int(blockDim.x);
-  SmemWalk<F> w{walk_smem + threadIdx.x, walk_smem + SmemWalk<F>::kAccChunks * nthr + threadIdx.x, nthr};
-  bool empty = true;
-  auto flush = [&](XYZZ<F>* dst) {
-    if (empty) XYZZ<F>::infinity().store(dst);
-    else w.load_all().store(dst);
-  };
-  uint32_t key_n = keys[start], val_n = vals[start];
-  w.prefetch(0, bases + (val_n & 0x7fffffffu));
-  uint32_t cur = key_n;
-  bool first_run = true;
-  int slot = 0;
-  for (uint64_t i = start; i < end; i++, slot ^= 1) {
-    uint32_t key = key_n, val = val_n;
-    cp_async_wait_all();                       // the point of this entry has landed
-    if (i + 1 < end) {
-      key_n = keys[i + 1];
-      val_n = vals[i + 1];
-      w.prefetch(slot ^ 1, bases + (val_n & 0x7fffffffu));
-    }
-    if (key != cur) {
-      if (first_run) {
-        part_keys[2 * tid] = cur;
-        flush(part_pts + 2 * tid);
-        first_run = false;
-      } else {
-        flush(buckets + cur);
-      }
-      empty = true;
-      cur = key;
-    }
-    w.madd(empty, slot, (val >> 31) != 0);
-  }
-  if (first_run) {
-    part_keys[2 * tid] = cur;
-    flush(part_pts + 2 * tid);
-    part_keys[2 * tid + 1] = kInvalidKey;
-  } else {
-    part_keys[2 * tid + 1] = cur;
-    flush(part_pts + 2 * tid + 1);
   }
 }
 
@@ -448,25 +302,10 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
                       void* bucket_target, cudaStream_t s) {
   using P = XYZZ<F>;
   cudaMemsetAsync(bucket_target, 0, p.n_buckets * sizeof(P), s);
-  if constexpr (L1Cfg<F>::kSmemWalk) {
-    constexpr size_t smem = size_t(SmemWalk<F>::kChunksPerThread) * 16 * 128;
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(msm_accumulate_l1_smem_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      cudaFuncSetAttribute(msm_accumulate_l1_smem_kernel<F>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      configured = true;
-    }
-    msm_accumulate_l1_smem_kernel<F><<<(p.l1_threads + 127) / 128, 128, smem, s>>>(
-        b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
-        reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
-        p.l1_threads);
-  } else {
-    msm_accumulate_l1_kernel<F><<<(p.l1_threads + 127) / 128, 128, 0, s>>>(
-        b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
-        reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
-        p.l1_threads);
-  }
+  msm_accumulate_l1_kernel<F><<<(p.l1_threads + 127) / 128, 128, 0, s>>>(
+      b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
+      reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
+      p.l1_threads);
   if (b.ev) cudaEventRecord(b.ev[3], s);
   msm_accumulate_l2_kernel<F><<<(p.l2_threads + 127) / 128, 128, 0, s>>>(
       b.part1_keys, reinterpret_cast<const P*>(b.part1_pts), 2 * p.l1_threads, p.l2_len,
