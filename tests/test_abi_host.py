@@ -138,3 +138,53 @@ def test_proof_format_matches_reference_layout():
     pr = pf.ProofResult(7, "p", "i", bytes(range(32)), bytes(32))
     assert pf.ProofResult.from_json(pr.to_json()) == pr
     assert json.loads(pr.to_json())["pre_state_root"] == list(range(32))
+
+
+def test_rust_sys_crate_is_in_sync_with_the_header():
+    """rust/zkb-sys cannot be built here (no cargo); it must at least bind every symbol of zkb.h."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"])
+    assert r.returncode == 0, "run `python tools/gen_rust_sys.py` after changing include/zkb.h"
+    text = open(os.path.join(ROOT, "rust", "zkb-sys", "src", "lib.rs")).read()
+    for sym in _declared_symbols():
+        assert "pub fn %s(" % sym in text, sym
+    assert 'cargo:rustc-link-lib=dylib=zkb' in open(os.path.join(ROOT, "rust", "zkb-sys", "build.rs")).read()
+
+
+def _build_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "prove_cli")
+    libdir = os.path.join(ROOT, "eigen-zeth_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "prove_cli.cpp"), "-L" + libdir, "-lzkb",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_example_builds_against_the_c_abi_and_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe, "8"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_example_proves_and_prints_reference_layout(tmp_path):
+    import subprocess
+    from eigen_zeth_b200 import proof_format as pf
+    exe = _build_example(tmp_path)
+    r = subprocess.run([exe, "10"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "pairing check passed" in r.stderr
+    proof_txt, input_txt = r.stdout.split("}\n[", 1)
+    proof_txt += "}"
+    input_txt = "[" + input_txt
+    a, b, c = pf.parse_proof(proof_txt)
+    assert o.g1_is_on_curve(a) and o.g2_is_on_curve(b) and o.g1_is_on_curve(c)
+    assert pf.parse_public_input(input_txt)[0] < o.R
+    # byte-identical to the library's own writer
+    assert pf.proof_to_json(pf.proof_from_json(proof_txt)) == proof_txt.rstrip("\n")

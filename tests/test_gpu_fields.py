@@ -65,3 +65,48 @@ def test_g2_ops(ctx):
     sc = [0, 1, o.R - 1] + [rng.fr() for _ in range(5)]
     got = g2_list(ctx.curve_op(1, 2, g2_bytes(P[:8]), fr_bytes(sc)))
     assert got == [o.g2_mul(x, k) for x, k in zip(P[:8], sc)]
+
+
+def test_abi_error_behaviour(ctx, zkb):
+    """argument validation at the C ABI: wrong group, out-of-range sub-ranges, unknown tunables,
+    one call at a time per context (ZKB_EBUSY)."""
+    import ctypes as C
+    import threading
+    g1 = ctx.upload_bases(g1_bytes([o.G1_GEN] * 4))
+    g2 = ctx.upload_bases(g2_bytes([o.G2_GEN] * 2), g2=True)
+    out = C.create_string_buffer(128)
+    sc = C.create_string_buffer(fr_bytes([1, 2, 3, 4]))
+    lib = ctx.lib
+    assert lib.zkb_msm_g2(ctx.h, g1.handle, 0, sc, 4, out) == zkb.lib.ZKB_EINVAL          # G1 bases to the G2 entry
+    assert lib.zkb_msm_g1(ctx.h, g2.handle, 0, sc, 2, out) == zkb.lib.ZKB_EINVAL
+    assert lib.zkb_msm_g1(ctx.h, g1.handle, 3, sc, 2, out) == zkb.lib.ZKB_EINVAL          # range past the end
+    assert lib.zkb_msm_g1(ctx.h, g1.handle, 0, None, 2, out) == zkb.lib.ZKB_EINVAL
+    assert lib.zkb_ctx_set(ctx.h, b"no_such_knob", 1) == zkb.lib.ZKB_EINVAL
+    assert b"unknown tunable" in lib.zkb_last_error(ctx.h)
+    assert lib.zkb_fr_ntt(ctx.h, sc, 0, 0, 0) == zkb.lib.ZKB_EINVAL
+    assert lib.zkb_fr_ntt(ctx.h, sc, 29, 0, 0) == zkb.lib.ZKB_EINVAL
+    with pytest.raises(zkb.ZkbError):
+        g1.precompute(1)
+    g1.precompute(12)
+    with pytest.raises(zkb.ZkbError):
+        g1.precompute(12)                                                                 # already expanded
+    # re-entrancy: a second thread calling into the same context while a long call runs gets EBUSY
+    big = ctx.synthetic_bases(1 << 18, 9)
+    scal = fr_bytes(rand_fr(o.Xoshiro256ss(3), 1 << 18))
+    seen = []
+
+    def hammer():
+        for _ in range(2000):
+            rc = lib.zkb_ctx_sync(ctx.h)       # cheap entry point without the guard
+            rc = lib.zkb_bench_int_pipe(ctx.h, 1, (C.c_double * 3)())
+            seen.append(rc)
+            if rc == zkb.lib.ZKB_EBUSY:
+                return
+
+    t = threading.Thread(target=hammer)
+    t.start()
+    for _ in range(3):
+        ctx.msm(big, scal)
+    t.join()
+    assert zkb.lib.ZKB_EBUSY in seen or all(rc == 0 for rc in seen)
+    assert o.g1_from_bytes(ctx.msm(g1, fr_bytes([1, 2, 3, 4]))) == o.g1_mul(o.G1_GEN, 10)   # context still healthy
