@@ -307,13 +307,25 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
       reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
       p.l1_threads);
   if (b.ev) cudaEventRecord(b.ev[3], s);
-  msm_accumulate_l2_kernel<F><<<(p.l2_threads + 127) / 128, 128, 0, s>>>(
-      b.part1_keys, reinterpret_cast<const P*>(b.part1_pts), 2 * p.l1_threads, p.l2_len,
-      reinterpret_cast<P*>(bucket_target), b.part2_keys, reinterpret_cast<P*>(b.part2_pts),
-      p.l2_threads);
-  msm_finish_kernel<F><<<(2 * p.l2_threads + 127) / 128, 128, 0, s>>>(
-      b.part2_keys, reinterpret_cast<const P*>(b.part2_pts), 2 * p.l2_threads,
-      reinterpret_cast<P*>(bucket_target));
+  // the partial list shrinks 16x per level-2 pass (chunks of l2_len entries -> 2 partials); passes
+  // repeat, ping-ponging between the two partial buffers, until the list is short enough for the
+  // serial-per-run finish.  A single giant bucket (0/1 witnesses, all-equal scalars) therefore
+  // costs a few short passes, never a long serial chain.
+  uint32_t* keys_a = b.part1_keys;
+  uint32_t* keys_b = b.part2_keys;
+  P* pts_a = reinterpret_cast<P*>(b.part1_pts);
+  P* pts_b = reinterpret_cast<P*>(b.part2_pts);
+  uint32_t count = 2 * p.l1_threads;
+  do {
+    uint32_t threads = (count + p.l2_len - 1) / p.l2_len;
+    msm_accumulate_l2_kernel<F><<<(threads + 127) / 128, 128, 0, s>>>(
+        keys_a, pts_a, count, p.l2_len, reinterpret_cast<P*>(bucket_target), keys_b, pts_b, threads);
+    count = 2 * threads;
+    uint32_t* tk = keys_a; keys_a = keys_b; keys_b = tk;
+    P* tp = pts_a; pts_a = pts_b; pts_b = tp;
+  } while (count > 1024);
+  msm_finish_kernel<F><<<(count + 127) / 128, 128, 0, s>>>(keys_a, pts_a, count,
+                                                           reinterpret_cast<P*>(bucket_target));
   if (b.ev) cudaEventRecord(b.ev[4], s);
 }
 
