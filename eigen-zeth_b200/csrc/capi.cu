@@ -862,15 +862,6 @@ void zkb_fr_root_of_unity(uint32_t log_n, int inverse, uint8_t out[32]) {
   a.to_bytes(out);
 }
 
-static bool all_canonical_fr(const uint8_t* data, uint64_t n) {
-  for (uint64_t i = 0; i < n; i++) {
-    uint64_t w[4];
-    std::memcpy(w, data + 32 * i, 32);
-    if (!HFr::lt_mod(w)) return false;
-  }
-  return true;
-}
-
 int zkb_fr_ntt(zkb_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, int coset) {
   if (!ctx) return ZKB_EINVAL;
   if (!data) return set_error(ctx, ZKB_EINVAL, "null buffer");

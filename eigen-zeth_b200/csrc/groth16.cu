@@ -722,14 +722,10 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
       break;
     }
     if (timings_opt) {
-      float* f[] = {&timings_opt->ms_h2d, &timings_opt->ms_spmv, &timings_opt->ms_ntt,
-                    &timings_opt->ms_msm_a, &timings_opt->ms_msm_b1, &timings_opt->ms_msm_b2,
-                    &timings_opt->ms_msm_l, &timings_opt->ms_msm_h};
       // stream order: START H2D SPMV NTT | A B1 L B2 (shared sort, charged to A) | H
       const int order[9] = {E_START, E_H2D, E_SPMV, E_NTT, E_A, E_B1, E_L, E_B2, E_H};
       float* g[] = {&timings_opt->ms_h2d, &timings_opt->ms_spmv, &timings_opt->ms_ntt, &timings_opt->ms_msm_a,
                     &timings_opt->ms_msm_b1, &timings_opt->ms_msm_l, &timings_opt->ms_msm_b2, &timings_opt->ms_msm_h};
-      (void)f;
       for (int i = 0; i < 8; i++) cudaEventElapsedTime(g[i], ev[order[i]], ev[order[i + 1]]);
       cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_H]);
     }
