@@ -236,7 +236,6 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     uint32_t CT = 8u << (8 - k);
     uint32_t tiles = uint32_t(total / M) * ((a.S + CT - 1) / CT);
     ntt_launch_pass(a, false, tiles, ctx->stream);
-    ctx->launches++;
     M >>= k;
     log_m -= k;
   }
@@ -260,7 +259,6 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     a.batch_log = log_n;
     a.tiles_per_batch = batch > 1 ? tiles : 0;
     ntt_launch_pass(a, true, uint32_t(tiles * batch), ctx->stream);
-    ctx->launches++;
   }
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
@@ -344,7 +342,6 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
   if ((rc = ensure_msm_buffers(ctx, p, &buf))) return rc;
   buf.result_affine = d_out_affine;
   if ((rc = msm_profile_events(ctx, &buf))) return rc;
-  ctx->launches += 8;   // digits, count_valid, L1, L2, finish, bucket_reduce, window_sum, horner
   // values index the whole base array: the sub-range starts at `first`
   msm_digits_and_sort(p, buf, d_scalars, n, uint32_t(first), ctx->stream);
   if (b->is_g2) {
@@ -389,7 +386,6 @@ int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* 
   if (any_g2 && (rc = ensure_msm_buffers(ctx, p2, &buf))) return rc;
   if ((rc = ensure_msm_buffers(ctx, p1, &buf))) return rc;
   msm_digits_and_sort(p1, buf, d_scalars, n, uint32_t(first), ctx->stream);
-  ctx->launches += 2;
   for (int j = 0; j < k; j++) {
     buf.result_affine = d_outs[j];
     if (bs[j]->is_g2) {
@@ -399,7 +395,6 @@ int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* 
       msm_accumulate_g1(p1, buf, bs[j]->d_pts, buf.buckets, ctx->stream);
       msm_tail_g1(p1, buf, ctx->stream);
     }
-    ctx->launches += 7;
     if (ev_opt) cudaEventRecord(ev_opt[j], ctx->stream);
   }
   ZKB_CUDA(ctx, cudaGetLastError());
@@ -467,11 +462,9 @@ int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_
       if (b->is_g2) msm_merge_g2(pk, buf.buckets, buf.buckets2, ctx->stream);
       else msm_merge_g1(pk, buf.buckets, buf.buckets2, ctx->stream);
     }
-    ctx->launches += 5 + (k ? 1 : 0);
   }
   if (b->is_g2) msm_tail_g2(p, buf, ctx->stream);
   else msm_tail_g1(p, buf, ctx->stream);
-  ctx->launches += 3;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -583,6 +576,7 @@ int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g
     fixed_base_mul_kernel<Fq><<<blocks, 128, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t*>(d_scalars), g1_generator_mont(),
         reinterpret_cast<Affine<Fq>*>(d_out), n);
+  count_launches(1);
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -601,7 +595,6 @@ int bases_precompute_nolock(zkb_ctx* ctx, zkb_bases* b, int c) {
   ZKB_CUDA(ctx, cudaMalloc(&d_new, b->n * nwin * sz));
   if (b->is_g2) msm_precompute_g2(b->d_pts, d_new, b->n, nwin, c, ctx->stream);
   else msm_precompute_g1(b->d_pts, d_new, b->n, nwin, c, ctx->stream);
-  ctx->launches++;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -629,6 +622,7 @@ int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint
   else
     bases_from_mont_kernel<Fq><<<blocks, 128, 0, ctx->stream>>>(
         reinterpret_cast<const Affine<Fq>*>(src), reinterpret_cast<Affine<Fq>*>(ctx->io_b.p), count);
+  count_launches(1);
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, count * sz, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;
@@ -810,7 +804,6 @@ int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, 
   ZKB_ENTER(ctx);
   if (!d_in || !d_out || d_in == d_out) return set_error(ctx, ZKB_EINVAL, "permute needs distinct buffers");
   fr_permute_launch(d_in, d_out, a, b, c, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -820,7 +813,6 @@ int zkb_fr_gather_layout_dev(zkb_ctx* ctx, const void* d_full, void* d_out, uint
   if (!d_full || !d_out || low_bits > log_n || world == 0 || rank >= world || ((1u << low_bits) % world))
     return set_error(ctx, ZKB_EINVAL, "bad layout argument");
   fr_gather_layout_launch(d_full, d_out, log_n, low_bits, world, rank, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -834,7 +826,6 @@ int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const ui
   hfr_to_words(b, bw);
   hfr_to_words(c, cw);
   fr_table_launch(d_out, bw, cw, rows, cols, row0, mul, mode, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -842,7 +833,6 @@ int zkb_fr_mul_sub_dev(zkb_ctx* ctx, void* d_a, const void* d_b, const void* d_c
   ZKB_ENTER(ctx);
   if (!d_a || !d_b || !d_c) return set_error(ctx, ZKB_EINVAL, "null buffer");
   fr_mul_sub_launch(d_a, d_b, d_c, n, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -850,7 +840,6 @@ int zkb_fr_convert_dev(zkb_ctx* ctx, void* d_data, uint64_t n, int to_montgomery
   ZKB_ENTER(ctx);
   if (!d_data) return set_error(ctx, ZKB_EINVAL, "null buffer");
   fr_convert_launch(d_data, n, to_montgomery, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -1076,7 +1065,6 @@ static int point_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d
   if (!d_out || (!d_points && n)) return set_error(ctx, ZKB_EINVAL, "null argument");
   if (is_g2) msm_sum_affine_g2(d_points, n, d_out, ctx->stream);
   else msm_sum_affine_g1(d_points, n, d_out, ctx->stream);
-  ctx->launches++;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -1087,7 +1075,7 @@ int zkb_g2_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out) 
   return point_sum_dev(ctx, d_points, n, d_out, 1);
 }
 
-uint64_t zkb_ctx_launches(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zkb_ctx_launches(const zkb_ctx* ctx) { return ctx ? launches_so_far() : 0; }
 
 int zkb_msm_last_timings(zkb_ctx* ctx, float ms_out[5]) {
   ZKB_ENTER(ctx);
@@ -1115,6 +1103,7 @@ int zkb_field_batch_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, const 
     field_batch_kernel<Fq><<<blocks, 128, 0, ctx->stream>>>(op, (const Fq*)ctx->io_a.p, b ? (const Fq*)ctx->io_b.p : nullptr, (Fq*)ctx->io_c.p, n);
   else
     field_batch_kernel<Fr><<<blocks, 128, 0, ctx->stream>>>(op, (const Fr*)ctx->io_a.p, b ? (const Fr*)ctx->io_b.p : nullptr, (Fr*)ctx->io_c.p, n);
+    count_launches(1);
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_c.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;
@@ -1138,6 +1127,7 @@ int zkb_curve_batch_op(zkb_ctx* ctx, int group, int op, const uint8_t* a, const 
     curve_batch_kernel<Fq><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<Fq>*)ctx->io_a.p, ctx->io_b.p, (Affine<Fq>*)ctx->io_c.p, n);
   else
     curve_batch_kernel<Fq2><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<Fq2>*)ctx->io_a.p, ctx->io_b.p, (Affine<Fq2>*)ctx->io_c.p, n);
+    count_launches(1);
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_c.p, n * aff, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;
@@ -1155,8 +1145,10 @@ int zkb_bench_int_pipe(zkb_ctx* ctx, int iters, double results[3]) {
   float ms = 0;
   // IMAD.WIDE carry chains: 32 wide-IMADs per inner iteration per thread
   imad_chain_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->io_a.p, iters / 8 + 1, 1, (long long*)ctx->io_c.p);
+  count_launches(1);
   cudaEventRecord(e0, ctx->stream);
   imad_chain_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->io_a.p, iters, 12345, (long long*)ctx->io_c.p);
+  count_launches(1);
   cudaEventRecord(e1, ctx->stream);
   ZKB_CUDA(ctx, cudaEventSynchronize(e1));
   cudaEventElapsedTime(&ms, e0, e1);
@@ -1166,8 +1158,10 @@ int zkb_bench_int_pipe(zkb_ctx* ctx, int iters, double results[3]) {
   results[2] = double(cycles) / (ms * 1e-3) / 1e6;
   // Montgomery multiplications: 4 per iteration per thread
   montmul_chain_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->io_a.p, iters / 8 + 1, 1);
+  count_launches(1);
   cudaEventRecord(e0, ctx->stream);
   montmul_chain_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->io_a.p, iters, 777);
+  count_launches(1);
   cudaEventRecord(e1, ctx->stream);
   ZKB_CUDA(ctx, cudaEventSynchronize(e1));
   cudaEventElapsedTime(&ms, e0, e1);

@@ -85,7 +85,6 @@ struct zkb_ctx {
   cudaEvent_t copy_ev[16] = {};
   cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool msm_ev_valid = false;
-  uint64_t launches = 0;                   // kernels of this library launched so far
 
   zkb::DevBuf stage_fwd, stage_inv;        // 255-entry stage twiddle tables
   std::map<uint64_t, zkb::NttDomain*> domains;   // key = log_n * 2 + inverse

@@ -679,6 +679,7 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     mark(E_H2D);
     const uint32_t bl_m = uint32_t((m + 255) / 256), bl_n = uint32_t((n + 255) / 256);
     fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
+    count_launches(5);   // + three SpMV launches and the pointwise kernel below
     void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
     for (int k = 0; k < 3; k++)
       r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
@@ -705,7 +706,6 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     }
     if ((rc = msm_exec(ctx, pk->h_query, 0, (const char*)pk->d_a + 32 * pk->qfirst[4], pk->qcount[4], res + 320))) break;
     mark(E_H);
-    ctx->launches += 5;   // to_mont copy, 3 x SpMV, pointwise (NTT/MSM count themselves)
     if (results_out_opt)
       cudaMemcpyAsync(results_out_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
     if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);
@@ -753,7 +753,7 @@ static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[
   groth16_assemble_kernel<<<1, 128, 0, st>>>((const uint8_t*)pk->d_results, (const uint8_t*)pk->d_fixed,
                                              (const uint32_t*)((char*)pk->d_proof + ZKB_PROOF_BYTES),
                                              (uint8_t*)pk->d_proof);
-  ctx->launches += 1;
+  count_launches(1);
   cudaMemcpyAsync(proof_out, pk->d_proof, ZKB_PROOF_BYTES, cudaMemcpyDeviceToHost, st);
   cudaEventRecord(e1, st);
   cudaError_t e = cudaStreamSynchronize(st);
@@ -776,6 +776,7 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
   ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st));
   const uint32_t bl_m = uint32_t((m + 255) / 256);
   fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
+  count_launches(4);   // + the three SpMV launches below
   void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
   uint64_t count = n;
   uint32_t lows = 0;
@@ -790,7 +791,6 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
                                          (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
                                          (Fr*)outs[k], pk->ncons, count, k == 0, pk->n_inst, pk->log_n,
                                          low_bits, lows, rank * lows);
-  ctx->launches += 4;
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }

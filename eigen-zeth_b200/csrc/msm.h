@@ -7,6 +7,11 @@
 
 namespace zkb {
 
+// kernels of this library launched by the process so far (every launch site adds its own count;
+// library kernels such as the CUB sort are not included)
+void count_launches(uint64_t k);
+uint64_t launches_so_far();
+
 struct MsmPlan {
   int c;                    // window width (signed digits in [-2^{c-1}, 2^{c-1}])
   uint32_t nwin;            // ceil(255 / c)

@@ -6,7 +6,13 @@
 
 #include "msm.h"
 
+#include <atomic>
+
 namespace zkb {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- 1. digits
 __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t c,
@@ -142,6 +148,7 @@ void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_sc
                                   (const uint32_t*)b.vals_in, b.vals_out, (int64_t)p.m, 0,
                                   p.key_bits, s);
   msm_count_valid_kernel<<<1, 1, 0, s>>>(b.keys_out, p.m, uint32_t(p.n_buckets), b.m_valid);
+  count_launches(blocks ? 2 : 1);
   if (b.ev) cudaEventRecord(b.ev[2], s);
 }
 

@@ -306,6 +306,7 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
       b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
       reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
       p.l1_threads);
+  count_launches(1);
   if (b.ev) cudaEventRecord(b.ev[3], s);
   // the partial list shrinks 16x per level-2 pass (chunks of l2_len entries -> 2 partials); passes
   // repeat, ping-ponging between the two partial buffers, until the list is short enough for the
@@ -320,12 +321,14 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
     uint32_t threads = (count + p.l2_len - 1) / p.l2_len;
     msm_accumulate_l2_kernel<F><<<(threads + 127) / 128, 128, 0, s>>>(
         keys_a, pts_a, count, p.l2_len, reinterpret_cast<P*>(bucket_target), keys_b, pts_b, threads);
+    count_launches(1);
     count = 2 * threads;
     uint32_t* tk = keys_a; keys_a = keys_b; keys_b = tk;
     P* tp = pts_a; pts_a = pts_b; pts_b = tp;
   } while (count > 1024);
   msm_finish_kernel<F><<<(count + 127) / 128, 128, 0, s>>>(keys_a, pts_a, count,
                                                            reinterpret_cast<P*>(bucket_target));
+  count_launches(1);
   if (b.ev) cudaEventRecord(b.ev[4], s);
 }
 
@@ -334,6 +337,7 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
   using P = XYZZ<F>;
   msm_bucket_merge_kernel<F><<<uint32_t((p.n_buckets + 127) / 128), 128, 0, s>>>(
       reinterpret_cast<P*>(main_buckets), reinterpret_cast<const P*>(part_buckets), p.n_buckets);
+  count_launches(1);
 }
 
 // bucket sums -> one point (Montgomery XYZZ + canonical affine)
@@ -361,6 +365,7 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
     msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(w0, groups, slices,
                                                                              slices > 1 ? stage : wl_out);
     if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, wl_out);
+    count_launches(slices > 1 ? 3 : 2);
     in = run_cursor;
     run_cursor += uint64_t(threads);
     count = groups;
@@ -372,6 +377,7 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
     msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(in, groups, slices,
                                                                              slices > 1 ? stage : s_tot);
     if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, s_tot);
+    count_launches(slices > 1 ? 3 : 2);   // + the Horner kernel below
   }
   msm_horner_kernel<F><<<1, 128, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,
                                          wl + uint64_t(p.red_levels + 1) * p.n_sets,
@@ -421,20 +427,26 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<F>* __
 template <class F>
 void msm_precompute_t(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s) {
   uint32_t blocks = uint32_t((n + 127) / 128);
-  if (blocks)
+  if (blocks) {
     msm_precompute_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<const Affine<F>*>(d_in),
                                                     reinterpret_cast<Affine<F>*>(d_out), n, nwin, c);
+    count_launches(1);
+  }
 }
 
 template <class F>
 void msm_bases_to_mont_t(void* d_pts, uint64_t n, cudaStream_t s) {
   uint32_t blocks = uint32_t((n + 127) / 128);
-  if (blocks) msm_bases_to_mont_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<Affine<F>*>(d_pts), n);
+  if (blocks) {
+    msm_bases_to_mont_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<Affine<F>*>(d_pts), n);
+    count_launches(1);
+  }
 }
 template <class F>
 void msm_sum_affine_t(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s) {
   msm_sum_affine_kernel<F><<<1, 32, 0, s>>>(reinterpret_cast<const Affine<F>*>(d_pts), n,
                                             reinterpret_cast<Affine<F>*>(d_out));
+  count_launches(1);
 }
 
 }  // namespace zkb

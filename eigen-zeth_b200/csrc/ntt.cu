@@ -382,6 +382,7 @@ void ntt_launch_pass(const NttPassArgs& a, bool final, uint32_t tiles, cudaStrea
     ntt_pass_kernel<true><<<tiles, kThreads, kSmemBytes, s>>>(a);
   else
     ntt_pass_kernel<false><<<tiles, kThreads, kSmemBytes, s>>>(a);
+  count_launches(1);
 }
 
 void fr_powers_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t count,
@@ -390,6 +391,7 @@ void fr_powers_launch(void* out, const uint32_t base[8], const uint32_t c[8], ui
   for (int i = 0; i < 8; i++) { b.v[i] = base[i]; cc.v[i] = c[i]; }
   uint32_t blocks = uint32_t((count + 255) / 256);
   if (blocks) fr_powers_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(out), b, cc, count, stride_pow);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t lo_bits,
@@ -399,6 +401,7 @@ void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t 
                                                 reinterpret_cast<const Fr*>(lo),
                                                 reinterpret_cast<const Fr*>(hi), lo_bits, tw_shift,
                                                 s_bits, M);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32_t C, cudaStream_t s) {
@@ -406,6 +409,7 @@ void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32
   uint32_t blocks = uint32_t((total + 255) / 256);
   if (blocks)
     fr_permute_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), A, B, C);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_gather_layout_launch(const void* full, void* out, uint32_t log_n, uint32_t d, uint32_t world,
@@ -416,6 +420,7 @@ void fr_gather_layout_launch(const void* full, void* out, uint32_t log_n, uint32
   if (blocks)
     fr_gather_layout_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(full),
                                                    reinterpret_cast<uint4*>(out), log_n, d, lows, rank * lows);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uint64_t rows, uint64_t cols,
@@ -424,6 +429,7 @@ void fr_table_launch(void* out, const uint32_t base[8], const uint32_t c[8], uin
   for (int i = 0; i < 8; i++) { b.v[i] = base[i]; cc.v[i] = c[i]; }
   uint32_t blocks = uint32_t((rows * cols + 255) / 256);
   if (blocks) fr_table_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(out), b, cc, rows, cols, row0, mul, mode);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_mul_sub_launch(void* a, const void* b, const void* c, uint64_t n, cudaStream_t s) {
@@ -431,11 +437,13 @@ void fr_mul_sub_launch(void* a, const void* b, const void* c, uint64_t n, cudaSt
   if (blocks)
     fr_mul_sub_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(a), reinterpret_cast<const Fr*>(b),
                                              reinterpret_cast<const Fr*>(c), n);
+  count_launches(blocks ? 1 : 0);
 }
 
 void fr_convert_launch(void* data, uint64_t n, int to_mont, cudaStream_t s) {
   uint32_t blocks = uint32_t((n + 255) / 256);
   if (blocks) fr_convert_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<Fr*>(data), n, to_mont);
+  count_launches(blocks ? 1 : 0);
 }
 
 }  // namespace zkb

@@ -6,6 +6,8 @@
 
 namespace zkb {
 
+void count_launches(uint64_t k);   // defined in msm_common.cu
+
 struct NttPassArgs {
   const void* in;          // n x 32 B
   void* out;               // n x 32 B (== in for the in-place column passes)

@@ -63,3 +63,17 @@ def test_ntt_rejects_bad_input(ctx, zkb):
         ctx.fr_ntt(int(o.R).to_bytes(32, "little") * 4)
     with pytest.raises(ValueError):
         ctx.fr_ntt(bytes(32 * 3))
+
+
+def test_launch_counter_counts_every_pass(ctx):
+    """zkb_ctx_launches feeds bench.py's gpu_launches claim: a resident Montgomery-form transform of
+    2^16 is exactly ceil(16/8) = 2 pass kernels once the tables exist."""
+    import torch
+    n = 1 << 16
+    x = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.fr_ntt_dev(x.data_ptr(), x.data_ptr(), 16, montgomery=True)     # builds the tables
+    ctx.sync()
+    before = ctx.launches
+    ctx.fr_ntt_dev(x.data_ptr(), x.data_ptr(), 16, montgomery=True)
+    ctx.sync()
+    assert ctx.launches - before == 2
