@@ -289,3 +289,39 @@ extern "C" int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t 
           miller(negp(C), delta, fr);
   return final_exp(f) == F12::one() ? ZKB_OK : ZKB_EVERIFY;
 }
+
+extern "C" int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_input[32],
+                               uint32_t* reasons_opt) {
+  if (!proof || !public_input) return ZKB_EINVAL;
+  uint32_t bad = 0;
+  auto all_zero = [](const uint8_t* b, int n) {
+    bool z = true;
+    for (int i = 0; i < n; i++) z = z && !b[i];
+    return z;
+  };
+  auto check_g1 = [&](const uint8_t* b, uint32_t range_bit, uint32_t curve_bit) {
+    if (all_zero(b, 64)) { bad |= ZKB_BAD_INFINITY; return; }
+    G1 p{HFq::zero(), HFq::zero(), false};
+    if (!read_fq(b, &p.x) || !read_fq(b + 32, &p.y)) { bad |= range_bit; return; }
+    if (!g1_on_curve(p)) bad |= curve_bit;   // BN254 G1 has cofactor 1: on-curve = in the group
+  };
+  check_g1(proof, ZKB_BAD_A_RANGE, ZKB_BAD_A_CURVE);
+  check_g1(proof + 192, ZKB_BAD_C_RANGE, ZKB_BAD_C_CURVE);
+  const uint8_t* b = proof + 64;
+  if (all_zero(b, 128)) {
+    bad |= ZKB_BAD_INFINITY;
+  } else {
+    G2 p{F2::zero(), F2::zero(), false};
+    if (!read_fq(b, &p.x.a) || !read_fq(b + 32, &p.x.b) || !read_fq(b + 64, &p.y.a) || !read_fq(b + 96, &p.y.b))
+      bad |= ZKB_BAD_B_RANGE;
+    else if (!g2_on_curve(p))
+      bad |= ZKB_BAD_B_CURVE;
+    else if (!g2_in_subgroup(p))
+      bad |= ZKB_BAD_B_SUBGROUP;
+  }
+  uint64_t x[4];
+  std::memcpy(x, public_input, 32);
+  if (!HFr::lt_mod(x)) bad |= ZKB_BAD_INPUT_RANGE;
+  if (reasons_opt) *reasons_opt = bad;
+  return bad ? ZKB_EINVAL : ZKB_OK;
+}

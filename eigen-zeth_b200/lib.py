@@ -24,7 +24,7 @@ EXPORTS = [
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
-    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify",
+    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_proof_check",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
@@ -115,6 +115,7 @@ def load_library() -> C.CDLL:
         lib.zkb_synthetic_witness.argtypes = [u32, u8p, u8p, vp]
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
+        lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
     lib.zkb_field_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_curve_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_bench_int_pipe.argtypes = [vp, i32, C.POINTER(C.c_double)]
@@ -463,3 +464,19 @@ def groth16_verify(vk: bytes, proof: bytes, public_input: bytes) -> bool:
     if rc == ZKB_EVERIFY:
         return False
     raise ZkbError(rc, "malformed verifying key / proof / input")
+
+
+PROOF_CHECK_REASONS = {
+    0x001: "pi_a coordinate >= q", 0x002: "pi_a not on the curve", 0x004: "pi_b coordinate >= q",
+    0x008: "pi_b not on the twist", 0x010: "pi_b outside the order-r subgroup", 0x020: "pi_c coordinate >= q",
+    0x040: "pi_c not on the curve", 0x080: "public input >= r", 0x100: "proof element is the point at infinity",
+}
+
+
+def proof_check(proof: bytes, public_input: bytes) -> list:
+    """strict well-formedness check (zkb_proof_check): [] when fine, else the list of reasons."""
+    if len(proof) != 256 or len(public_input) != 32:
+        raise ValueError("proof is 256 bytes, public input 32")
+    bits = C.c_uint32(0)
+    load_library().zkb_proof_check(proof, public_input, C.byref(bits))
+    return [msg for bit, msg in PROOF_CHECK_REASONS.items() if bits.value & bit]

@@ -83,11 +83,7 @@ def parse_public_input(json_str: str):
 
 
 def proof_from_json(json_str: str) -> bytes:
-    a, b, c = parse_proof(json_str)
-    vals = [a[0], a[1], b[0][0], b[0][1], b[1][0], b[1][1], c[0], c[1]]
-    if any(x >= Q for x in vals):
-        raise ValueError("coordinate not reduced modulo q")
-    return b"".join(x.to_bytes(32, "little") for x in vals)
+    return _coords_to_bytes(parse_proof(json_str))
 
 
 def public_input_from_json(json_str: str) -> bytes:
@@ -95,6 +91,32 @@ def public_input_from_json(json_str: str) -> bytes:
     if x >= R:
         raise ValueError("public input not reduced modulo r")   # NewStateRootNotInsidePrime on-chain
     return x.to_bytes(32, "little")
+
+
+def validate_final_proof(proof_json: str, public_input_json: str) -> None:
+    """Strict gate in front of `verify_batches`.  The reference's own readers
+    (ethereum/mod.rs:445-481) accept any U256 and only element 0 of the input array; the contract then
+    reverts with InvalidProof / NewStateRootNotInsidePrime (interfaces/zkvm.rs:82-130) after the L1
+    transaction was sent.  This check raises ValueError before that: the JSON must parse the way
+    parse_proof parses it, hold exactly one public input (`uint256[1]`), every coordinate < q, the
+    input < r, pi_a / pi_c on the curve, pi_b on the twist and in the order-r subgroup, and no
+    element at infinity.  The group checks run in libzkb.so (zkb_proof_check, host code)."""
+    v = json.loads(public_input_json)
+    if not isinstance(v, list) or len(v) != 1:
+        raise ValueError("public_input.json must be an array of exactly one decimal string")
+    from . import lib
+    reasons = lib.proof_check(_coords_to_bytes(parse_proof(proof_json), clamp=True),
+                              min(parse_public_input(public_input_json)[0], (1 << 256) - 1).to_bytes(32, "little"))
+    if reasons:
+        raise ValueError("malformed final proof: " + "; ".join(reasons))
+
+
+def _coords_to_bytes(parsed, clamp=False) -> bytes:
+    a, b, c = parsed
+    vals = [a[0], a[1], b[0][0], b[0][1], b[1][0], b[1][1], c[0], c[1]]
+    if not clamp and any(x >= Q for x in vals):
+        raise ValueError("coordinate not reduced modulo q")
+    return b"".join(x.to_bytes(32, "little") for x in vals)
 
 
 def vk_to_json(vk: bytes) -> str:

@@ -83,7 +83,9 @@ class GpuGroth16Backend:
         public_input = witness[32:64]
         if self.self_check and not self.lib.groth16_verify(self.pk.vk, proof, public_input):
             raise RuntimeError("pairing check failed on a freshly generated proof")
-        return proof_format.proof_to_json(proof), proof_format.public_input_to_json(public_input), timings
+        proof_json, input_json = proof_format.proof_to_json(proof), proof_format.public_input_to_json(public_input)
+        proof_format.validate_final_proof(proof_json, input_json)     # what leaves is what verify_batches will accept
+        return proof_json, input_json, timings
 
 
 class ProverServicer:

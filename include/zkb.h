@@ -195,6 +195,22 @@ int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_
  * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
 int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],
                        const uint8_t public_input[32]);
+/* Strict well-formedness check of a proof / public input pair BEFORE it is handed to the settlement
+ * layer (CPU, needs no key): the reference's parse_proof (src/settlement/ethereum/mod.rs:445-473)
+ * accepts any U256, the contract then reverts (InvalidProof / NewStateRootNotInsidePrime,
+ * src/settlement/ethereum/interfaces/zkvm.rs:82-130) after the L1 transaction has been paid for.
+ * Returns ZKB_OK, or ZKB_EINVAL with *reasons_opt = OR of the ZKB_BAD_* bits below. */
+#define ZKB_BAD_A_RANGE 0x001u     /* a coordinate of pi_a is >= q */
+#define ZKB_BAD_A_CURVE 0x002u     /* pi_a is not on y^2 = x^3 + 3 */
+#define ZKB_BAD_B_RANGE 0x004u
+#define ZKB_BAD_B_CURVE 0x008u     /* pi_b is not on the twist y^2 = x^3 + 3/(9+u) */
+#define ZKB_BAD_B_SUBGROUP 0x010u  /* on the twist but outside the order-r subgroup */
+#define ZKB_BAD_C_RANGE 0x020u
+#define ZKB_BAD_C_CURVE 0x040u
+#define ZKB_BAD_INPUT_RANGE 0x080u /* public input >= r */
+#define ZKB_BAD_INFINITY 0x100u    /* a proof element is the point at infinity (all-zero encoding) */
+int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_input[32],
+                    uint32_t* reasons_opt);
 
 /* ---- test / measurement hooks ------------------------------------------------------------------ */
 /* element-wise field ops on host arrays of canonical elements, executed by the device field

@@ -95,6 +95,7 @@ extern "C" {
     pub fn zkb_groth16_msm_dev(ctx: *mut zkb_ctx, pk: *const zkb_pk, d_h: *const c_void, partial_out: *mut u8) -> c_int;
     pub fn zkb_groth16_assemble(ctx: *mut zkb_ctx, pk: *const zkb_pk, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
     pub fn zkb_groth16_verify(vk: *const u8, proof: *const u8, public_input: *const u8) -> c_int;
+    pub fn zkb_proof_check(proof: *const u8, public_input: *const u8, reasons_opt: *mut u32) -> c_int;
     pub fn zkb_field_batch_op(ctx: *mut zkb_ctx, field: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_curve_batch_op(ctx: *mut zkb_ctx, group: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_bench_int_pipe(ctx: *mut zkb_ctx, iters: c_int, results: *mut f64) -> c_int;

@@ -140,6 +140,69 @@ def test_proof_format_matches_reference_layout():
     assert json.loads(pr.to_json())["pre_state_root"] == list(range(32))
 
 
+def _f2_sqrt(a):
+    """square root in Fq[u]/(u^2+1), q = 3 mod 4 (test helper)."""
+    q = o.Q
+    rt = lambda v: (lambda r: r if r * r % q == v % q else None)(pow(v, (q + 1) // 4, q))
+    if a[1] == 0:
+        r = rt(a[0])
+        return (r, 0) if r is not None else (0, rt(-a[0] % q))
+    s = rt((a[0] * a[0] + a[1] * a[1]) % q)
+    if s is None:
+        return None
+    inv2 = pow(2, q - 2, q)
+    x0 = rt((a[0] + s) * inv2 % q)
+    if x0 is None:
+        x0 = rt((a[0] - s) * inv2 % q)
+    if x0 is None:
+        return None
+    y = (x0, a[1] * pow(2 * x0, q - 2, q) % q)
+    return y if o.f2_sqr(y) == (a[0] % q, a[1] % q) else None
+
+
+def test_strict_final_proof_validator(zkb):
+    """the gate in front of verify_batches.  All three reference fixtures are well-formed
+    group elements (Appendix C); every class of malformation is named."""
+    from eigen_zeth_b200 import proof_format as pf
+    for key in ("proof_json", "test_parse_proof_json", "worker_compact_proof_json"):
+        pf.validate_final_proof(GOLDEN[key], GOLDEN["public_input_json"])
+    raw = pf.proof_from_json(GOLDEN["proof_json"])
+    pub = pf.public_input_from_json(GOLDEN["public_input_json"])
+    assert zkb.proof_check(raw, pub) == []
+    le = lambda v: int(v).to_bytes(32, "little")
+    # pi_a: y + 1 leaves the curve; x >= q is a range error (parse_proof itself would accept both)
+    bad = raw[:32] + le(int.from_bytes(raw[32:64], "little") + 1) + raw[64:]
+    assert zkb.proof_check(bad, pub) == ["pi_a not on the curve"]
+    bad = le(int.from_bytes(raw[:32], "little") + o.Q) + raw[32:]
+    assert zkb.proof_check(bad, pub) == ["pi_a coordinate >= q"]
+    # pi_b with c0 / c1 swapped (the snarkjs-vs-contract ordering mistake): off the twist
+    sw = raw[:64] + raw[96:128] + raw[64:96] + raw[160:192] + raw[128:160] + raw[192:]
+    assert zkb.proof_check(sw, pub) == ["pi_b not on the twist"]
+    # a twist point outside the order-r subgroup: x = 1 + 0u gives one after clearing nothing
+    x = 0
+    while True:
+        x += 1
+        y = _f2_sqrt(o.f2_add(o.f2_mul(o.f2_sqr((x, 0)), (x, 0)), o.TWIST_B))
+        if y is not None and not o.g2_in_subgroup(((x, 0), y)):
+            break
+    cof = raw[:64] + le(x) + le(0) + le(y[0]) + le(y[1]) + raw[192:]
+    assert zkb.proof_check(cof, pub) == ["pi_b outside the order-r subgroup"]
+    # pi_c at infinity, input >= r, both reported together
+    assert zkb.proof_check(raw[:192] + bytes(64), le(o.R)) == ["public input >= r", "proof element is the point at infinity"]
+    # the JSON-level gate: two inputs, oversized input, tampered coordinate
+    with pytest.raises(ValueError, match="exactly one"):
+        pf.validate_final_proof(GOLDEN["proof_json"], '["1","2"]')
+    with pytest.raises(ValueError, match="public input >= r"):
+        pf.validate_final_proof(GOLDEN["proof_json"], '["%d"]' % o.R)
+    doc = json.loads(GOLDEN["proof_json"])
+    doc["pi_c"]["y"] = str(int(doc["pi_c"]["y"]) ^ 1)
+    with pytest.raises(ValueError, match="pi_c not on the curve"):
+        pf.validate_final_proof(json.dumps(doc), GOLDEN["public_input_json"])
+    doc["pi_c"]["y"] = str((1 << 256) - 1)
+    with pytest.raises(ValueError, match="pi_c coordinate >= q"):
+        pf.validate_final_proof(json.dumps(doc), GOLDEN["public_input_json"])
+
+
 def test_rust_sys_crate_is_in_sync_with_the_header():
     """rust/zkb-sys cannot be built here (no cargo); it must at least bind every symbol of zkb.h."""
     import subprocess
