@@ -25,6 +25,7 @@ EXPORTS = [
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
     "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_proof_check",
+    "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings",
 ]
@@ -53,6 +54,12 @@ class ProveTimings(C.Structure):
 
 
 _lib = None
+
+
+class R1csInfo(C.Structure):
+    _fields_ = [("n_wires", C.c_uint32), ("n_pub_out", C.c_uint32), ("n_pub_in", C.c_uint32),
+                ("n_prv_in", C.c_uint32), ("n_constraints", C.c_uint32), ("n_labels", C.c_uint64),
+                ("nnz", C.c_uint64 * 3)]
 
 
 def load_library() -> C.CDLL:
@@ -116,6 +123,10 @@ def load_library() -> C.CDLL:
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
         lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
+    lib.zkb_r1cs_inspect.argtypes = [u8p, u64, C.POINTER(R1csInfo)]
+    lib.zkb_r1cs_read.argtypes = [u8p, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.zkb_wtns_inspect.argtypes = [u8p, u64, C.POINTER(u32)]
+    lib.zkb_wtns_read.argtypes = [u8p, u64, vp]
     lib.zkb_field_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_curve_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_bench_int_pipe.argtypes = [vp, i32, C.POINTER(C.c_double)]

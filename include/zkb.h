@@ -212,6 +212,25 @@ int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_P
 int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_input[32],
                     uint32_t* reasons_opt);
 
+/* ---- circuit files -------------------------------------------------------------
+ * Readers for the iden3 binary formats circom / snarkjs write (.r1cs constraint systems, .wtns
+ * witnesses) over BN254's scalar field; host code, no allocation.  Wire order is
+ * (1, public outputs, public inputs, private inputs) = the z order of zkb_pk_desc, with
+ * n_public = n_pub_out + n_pub_in.  Two-pass: inspect sizes the caller's buffers, read fills them
+ * (row_ptr[k]: n_constraints + 1 entries, col[k]: nnz[k], coeff[k]: 32 * nnz[k] bytes, canonical).
+ * ZKB_EINVAL for a bad magic / version / truncated section / another prime / a wire index out of
+ * range / a non-canonical value / a witness whose wire 0 is not 1. */
+typedef struct zkb_r1cs_info {
+  uint32_t n_wires, n_pub_out, n_pub_in, n_prv_in, n_constraints;
+  uint64_t n_labels;
+  uint64_t nnz[3];   /* non-zeros of A, B, C */
+} zkb_r1cs_info;
+int zkb_r1cs_inspect(const uint8_t* file, uint64_t len, zkb_r1cs_info* out);
+int zkb_r1cs_read(const uint8_t* file, uint64_t len, uint32_t* const row_ptr[3], uint32_t* const col[3],
+                  uint8_t* const coeff[3]);
+int zkb_wtns_inspect(const uint8_t* file, uint64_t len, uint32_t* n_witness_out);
+int zkb_wtns_read(const uint8_t* file, uint64_t len, uint8_t* witness_out);
+
 /* ---- test / measurement hooks ------------------------------------------------------------------ */
 /* element-wise field ops on host arrays of canonical elements, executed by the device field
  * library: field 0 = Fq, 1 = Fr; op 0 add, 1 sub, 2 mul, 3 sqr, 4 inverse, 5 neg,

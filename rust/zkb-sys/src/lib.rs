@@ -22,6 +22,16 @@ pub const ZKB_EVERIFY: c_int = -6;
 pub const ZKB_VK_BYTES: usize = 576;
 pub const ZKB_PROOF_BYTES: usize = 256;
 pub const ZKB_INTERMEDIATE_BYTES: usize = 384;
+// reason bits of zkb_proof_check
+pub const ZKB_BAD_A_RANGE: u32 = 0x001;
+pub const ZKB_BAD_A_CURVE: u32 = 0x002;
+pub const ZKB_BAD_B_RANGE: u32 = 0x004;
+pub const ZKB_BAD_B_CURVE: u32 = 0x008;
+pub const ZKB_BAD_B_SUBGROUP: u32 = 0x010;
+pub const ZKB_BAD_C_RANGE: u32 = 0x020;
+pub const ZKB_BAD_C_CURVE: u32 = 0x040;
+pub const ZKB_BAD_INPUT_RANGE: u32 = 0x080;
+pub const ZKB_BAD_INFINITY: u32 = 0x100;
 
 #[repr(C)]
 #[derive(Debug, Default, Clone, Copy)]
@@ -44,6 +54,15 @@ pub struct zkb_pk_desc {
     pub l_query: *const u8, pub h_query: *const u8,
     pub alpha_g1: *const u8, pub beta_g1: *const u8, pub delta_g1: *const u8,
     pub beta_g2: *const u8, pub delta_g2: *const u8,
+}
+
+/// sizes of an iden3 .r1cs file (see include/zkb.h `zkb_r1cs_info`)
+#[repr(C)]
+#[derive(Debug, Default, Clone, Copy)]
+pub struct zkb_r1cs_info {
+    pub n_wires: u32, pub n_pub_out: u32, pub n_pub_in: u32, pub n_prv_in: u32, pub n_constraints: u32,
+    pub n_labels: u64,
+    pub nnz: [u64; 3],
 }
 
 #[link(name = "zkb")]
@@ -96,6 +115,10 @@ extern "C" {
     pub fn zkb_groth16_assemble(ctx: *mut zkb_ctx, pk: *const zkb_pk, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
     pub fn zkb_groth16_verify(vk: *const u8, proof: *const u8, public_input: *const u8) -> c_int;
     pub fn zkb_proof_check(proof: *const u8, public_input: *const u8, reasons_opt: *mut u32) -> c_int;
+    pub fn zkb_r1cs_inspect(file: *const u8, len: u64, out_: *mut zkb_r1cs_info) -> c_int;
+    pub fn zkb_r1cs_read(file: *const u8, len: u64, row_ptr: *mut *mut u32, col: *mut *mut u32, coeff: *mut *mut u8) -> c_int;
+    pub fn zkb_wtns_inspect(file: *const u8, len: u64, n_witness_out: *mut u32) -> c_int;
+    pub fn zkb_wtns_read(file: *const u8, len: u64, witness_out: *mut u8) -> c_int;
     pub fn zkb_field_batch_op(ctx: *mut zkb_ctx, field: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_curve_batch_op(ctx: *mut zkb_ctx, group: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_bench_int_pipe(ctx: *mut zkb_ctx, iters: c_int, results: *mut f64) -> c_int;

@@ -212,6 +212,12 @@ def test_rust_sys_crate_is_in_sync_with_the_header():
     text = open(os.path.join(ROOT, "rust", "zkb-sys", "src", "lib.rs")).read()
     for sym in _declared_symbols():
         assert "pub fn %s(" % sym in text, sym
+    import re
+    hdr = open(os.path.join(ROOT, "include", "zkb.h")).read()
+    for name in re.findall(r"typedef struct (zkb_[a-z0-9_]+)", hdr):
+        assert "pub struct %s " % name in text, name
+    for name in re.findall(r"#define (ZKB_[A-Z0-9_]+) ", hdr):
+        assert "pub const %s:" % name in text, name
     assert 'cargo:rustc-link-lib=dylib=zkb' in open(os.path.join(ROOT, "rust", "zkb-sys", "build.rs")).read()
 
 

@@ -148,3 +148,33 @@ def test_pk_load_external_circuit(ctx, zkb, log_n):
         ctx.pk_load(log_n, cs["m"], cs["n_pub"], bad, queries, opk.fixed())
     pk.free()
     opk.free()
+
+
+@pytest.mark.parametrize("n_constraints", [6, 27])
+def test_circuit_from_r1cs_and_wtns_files(ctx, zkb, n_constraints):
+    """a circuit that is not the synthetic chain arrives as iden3 .r1cs / .wtns bytes
+    (wire count and constraint count not powers of two), is parsed by libzkb.so, keyed by oracle A's
+    general ark-groth16 setup and proved on the GPU; proof = oracle A's proof, byte for byte."""
+    from eigen_zeth_b200 import circom_io as cio
+    from helpers import small_circuit
+    cs, z = small_circuit(n_constraints)
+    r1 = cio.read_r1cs(cio.write_r1cs(cs["m"], 1, 0, 2, list(zip(cs["A"], cs["B"], cs["C"])), header_last=bool(n_constraints & 1)))
+    wit = cio.read_wtns(cio.write_wtns(z))
+    assert len(wit) == 32 * r1.n_wires
+    rng = o.Xoshiro256ss(0xC1C0 + n_constraints)
+    tau, alpha, beta, gamma, delta, r, s = [rng.fr() or 1 for _ in range(7)]
+    opk, ovk = o.groth16_setup(cs, tau, alpha, beta, gamma, delta)
+    g1s = lambda pts: b"".join(o.g1_to_bytes(P) for P in pts)
+    queries = {"a_query": g1s(opk["a_query"]), "b_g1_query": g1s(opk["b_g1_query"]),
+               "b_g2_query": b"".join(o.g2_to_bytes(P) for P in opk["b_g2_query"]),
+               "l_query": g1s(opk["l_query"]), "h_query": g1s(opk["h_query"])}
+    fixed = {"alpha_g1": o.g1_to_bytes(opk["alpha_g1"]), "beta_g1": o.g1_to_bytes(opk["beta_g1"]),
+             "delta_g1": o.g1_to_bytes(opk["delta_g1"]), "beta_g2": o.g2_to_bytes(opk["beta_g2"]),
+             "delta_g2": o.g2_to_bytes(opk["delta_g2"])}
+    assert (1 << r1.log_n) == o.domain_size(cs)
+    pk = ctx.pk_load(r1.log_n, r1.n_wires, r1.n_public, r1.matrices, queries, fixed)
+    proof, _, _, _ = ctx.groth16_prove(pk, wit, r.to_bytes(32, "little"), s.to_bytes(32, "little"))
+    (A, B, C), _ = o.groth16_prove(opk, cs, z, r, s)
+    assert proof == o.g1_to_bytes(A) + o.g2_to_bytes(B) + o.g1_to_bytes(C)
+    assert o.groth16_verify(ovk, (A, B, C), [z[1]])
+    pk.free()
