@@ -148,7 +148,7 @@ def run_reference(args):
     value = n * args.steps / inner / 1e6
     sample = "each step: one 2^%d-point G1 MSM (bounded sample of the 2^%d workload), %d host threads" % (
         CPU_SAMPLE_LOG, LOG_N, ob.threads())
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * inner / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)",
@@ -157,10 +157,31 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": ob.threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
-    }))
+    })
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON result).  Libraries underneath write to fd 1 on their
+    own (NCCL prints its version banner there): keep a private handle on the real stdout and point
+    fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -413,7 +434,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
