@@ -88,11 +88,56 @@ class GpuGroth16Backend:
         return proof_json, input_json, timings
 
 
+class BatchLedger:
+    """Per-batch bookkeeping across the four steps.  The client carries
+    task_id / chunk_count / batch_data from one response into the next request
+    (provider.rs:340-377) and, after a restart, re-enters at whatever step it had persisted with the
+    same batch_id (provider.rs:245-274).  So: a step for an unknown batch is accepted (this server may
+    have restarted too), a step for a known batch must agree with what was handed out earlier, and
+    every step is idempotent.  Bounded LRU; thread-safe (several operator streams share it)."""
+
+    STEPS = ("chunks", "chunk_proofs", "aggregated", "final")
+
+    def __init__(self, capacity=1024):
+        self._lock = threading.Lock()
+        self._rows = OrderedDict()
+        self._capacity = capacity
+
+    def record(self, batch_id: str, step: str, **facts):
+        """-> None when consistent, else a message naming the mismatch."""
+        with self._lock:
+            row = self._rows.get(batch_id)
+            if row is None:
+                row = self._rows[batch_id] = {"steps": {}, "facts": {}}
+            self._rows.move_to_end(batch_id)
+            for k, v in facts.items():
+                old = row["facts"].get(k)
+                if old is not None and old != v:
+                    return "batch %s: %s was %r, request says %r" % (batch_id, k, old, v)
+            row["facts"].update(facts)
+            row["steps"][step] = row["steps"].get(step, 0) + 1
+            while len(self._rows) > self._capacity:
+                self._rows.popitem(last=False)
+        return None
+
+    def view(self, batch_id: str):
+        with self._lock:
+            row = self._rows.get(batch_id)
+            return None if row is None else {"steps": dict(row["steps"]), "facts": dict(row["facts"])}
+
+    def __len__(self):
+        with self._lock:
+            return len(self._rows)
+
+
 class ProverServicer:
     """the stream handler; `backend` only needs .final_proof(batch_id, recursive_proof, aggregator_addr)."""
 
     def __init__(self, backend, prover_name="zkb-b200", cache_size=64):
         self.backend = backend
+        self.ledger = BatchLedger()
+        self.queued = 0                           # GenFinalProof requests waiting for / on the GPU (all streams)
+        self._count_lock = threading.Lock()
         self.prover_name = prover_name
         self.prover_id = hashlib.sha256(("%s-%d" % (prover_name, os.getpid())).encode()).hexdigest()[:16]
         self._lock = threading.Lock()            # one proof at a time per server
@@ -107,13 +152,23 @@ class ProverServicer:
     def _gen_batch_chunks(self, req):
         blocks = list(req.batch.block_number)
         task_id = "%010d" % (blocks[0] if blocks else 0)
+        batch_data = json.dumps({"blocks": blocks, "chain_id": req.chain_id, "program": req.program_name})
+        bad = self.ledger.record(req.batch_id, "chunks", task_id=task_id, chunk_count=2, batch_data=batch_data)
+        if bad:        # the same batch_id re-submitted with other blocks: refuse rather than prove the wrong thing
+            return pb.GenBatchProofResponse(gen_batch_chunks=pb.GenBatchChunksResult(
+                batch_id=req.batch_id, result_code=pb.COMPLETED_ERROR, error_message=bad,
+                pre_state_root=bytes(32), post_state_root=bytes(32)))
         res = pb.GenBatchChunksResult(
-            batch_id=req.batch_id, task_id=task_id, result_code=pb.COMPLETED_OK, chunk_count=2,
-            batch_data=json.dumps({"blocks": blocks, "chain_id": req.chain_id, "program": req.program_name}),
+            batch_id=req.batch_id, task_id=task_id, result_code=pb.COMPLETED_OK, chunk_count=2, batch_data=batch_data,
             pre_state_root=_h("pre", req.chain_id, *blocks), post_state_root=_h("post", req.chain_id, *blocks))
         return pb.GenBatchProofResponse(gen_batch_chunks=res)
 
     def _gen_chunk_proof(self, req):
+        bad = self.ledger.record(req.batch_id, "chunk_proofs", task_id=req.task_id, chunk_count=int(req.chunk_count),
+                                 batch_data=req.batch_data)
+        if bad:
+            return pb.GenBatchProofResponse(gen_chunk_proof=pb.GenChunkProofResult(
+                batch_id=req.batch_id, task_id=req.task_id, result_code=pb.COMPLETED_ERROR, error_message=bad))
         n = max(1, int(req.chunk_count))
         proofs = [pb.ChunkProof(chunk_id=i, proof_key="%s-%d" % (req.task_id, i),
                                 proof=_h("chunk", req.batch_id, req.batch_data, i).hex()) for i in range(n)]
@@ -122,6 +177,7 @@ class ProverServicer:
         return pb.GenBatchProofResponse(gen_chunk_proof=res)
 
     def _gen_aggregated(self, req):
+        self.ledger.record(req.batch_id, "aggregated")
         return pb.GenAggregatedProofResponse(
             batch_id=req.batch_id, result_code=pb.COMPLETED_OK,
             result_string=_h("agg", req.recursive_proof_1, req.recursive_proof_2).hex())
@@ -132,6 +188,18 @@ class ProverServicer:
             return pb.GenFinalProofResponse(batch_id=req.batch_id, result_code=pb.COMPLETED_ERROR,
                                             error_message="unsupported curve %r (only BN128)" % req.curve_name)
         key = (req.batch_id, req.recursive_proof, req.aggregator_addr)
+        # no consistency facts here: a re-aggregated batch may legitimately carry another recursive
+        # proof, and an error would make the client resend the same request forever (provider.rs:511-516)
+        self.ledger.record(req.batch_id, "final")
+        with self._count_lock:
+            self.queued += 1                      # streams queue here: one proof at a time on the GPU
+        try:
+            return self._gen_final_locked(req, request_id, key)
+        finally:
+            with self._count_lock:
+                self.queued -= 1
+
+    def _gen_final_locked(self, req, request_id, key):
         with self._lock:
             hit = self._cache.get(key)
             if hit is None:

@@ -92,6 +92,68 @@ def test_errors_keep_the_stream_open(server):
     op.close()
 
 
+def test_batch_ledger_and_concurrent_streams(server):
+    """per-batch bookkeeping, idempotent replay of every step, several operator streams
+    queueing on one prover."""
+    import threading
+    import time
+    from operator_replay import OperatorReplay
+    from eigen_zeth_b200 import protocol as pb
+    addr, backend, servicer = server
+    op = OperatorReplay(addr, step_sleep=0.0)
+    res, _ = op.execute(block_number=11, batch_id="ledger-1")
+    row = servicer.ledger.view("ledger-1")
+    assert row["steps"] == {"chunks": 1, "chunk_proofs": 1, "aggregated": 1, "final": 1}
+    assert row["facts"]["chunk_count"] == 2 and json.loads(row["facts"]["batch_data"])["blocks"] == [11]
+    op.execute(block_number=11, batch_id="ledger-1")                 # full replay: every step counted twice, no error
+    assert servicer.ledger.view("ledger-1")["steps"]["chunks"] == 2
+    # a chunk-proof request that contradicts what GenBatchChunks handed out is refused (and the stream survives)
+    bad = pb.ProverRequest(id="x", gen_batch_proof=pb.GenBatchProofRequest(gen_chunk_proof=pb.GenChunkProof(
+        batch_id="ledger-1", task_id=row["facts"]["task_id"], chunk_count=5, batch_data=row["facts"]["batch_data"])))
+    r = servicer.handle(bad)
+    assert r.gen_batch_proof.gen_chunk_proof.result_code == pb.COMPLETED_ERROR
+    assert "chunk_count" in r.gen_batch_proof.gen_chunk_proof.error_message
+    # ... the same batch id re-submitted with other blocks likewise
+    with pytest.raises(AssertionError):          # the replay client asserts COMPLETED_OK on this step
+        op.execute(block_number=12, batch_id="ledger-1")
+    # a step for a batch this server has never seen (server restart) is accepted
+    ok = pb.ProverRequest(id="y", gen_batch_proof=pb.GenBatchProofRequest(gen_chunk_proof=pb.GenChunkProof(
+        batch_id="after-restart", task_id="0000000001", chunk_count=3, batch_data="{}")))
+    r = servicer.handle(ok)
+    assert r.gen_batch_proof.gen_chunk_proof.result_code == pb.COMPLETED_OK
+    assert len(r.gen_batch_proof.gen_chunk_proof.batch_proof_result.chunk_proofs) == 3
+    op.close()
+
+    # four operator streams at once against one (slow) prover: all served, proofs never overlap
+    state = {"inside": 0, "max_inside": 0}
+    real = backend.final_proof
+
+    def slow(*a):
+        state["inside"] += 1
+        state["max_inside"] = max(state["max_inside"], state["inside"])
+        time.sleep(0.05)
+        state["inside"] -= 1
+        return real(*a)
+
+    backend.final_proof = slow
+    results, errors = {}, []
+
+    def one(k):
+        try:
+            o_ = OperatorReplay(addr, step_sleep=0.0)
+            results[k] = o_.execute(block_number=100 + k, batch_id="stream-%d" % k)[0]
+            o_.close()
+        except Exception as ex:
+            errors.append(ex)
+
+    threads = [threading.Thread(target=one, args=(k,)) for k in range(4)]
+    [t.start() for t in threads]
+    [t.join(timeout=30) for t in threads]
+    assert not errors and sorted(results) == [0, 1, 2, 3]
+    assert [results[k].block_number for k in range(4)] == [100, 101, 102, 103]
+    assert state["max_inside"] == 1 and servicer.queued == 0
+
+
 @pytest.mark.gpu
 def test_service_proves_on_gpu_and_verifies():
     from operator_replay import OperatorReplay
