@@ -162,3 +162,18 @@ def test_precomputed_g2_and_large_closed_form(ctx):
         assert o.g1_from_bytes(ctx.msm(big, fr_bytes(sc))) == want
     finally:
         ctx.set("msm_host_chunks", 0)
+    # skewed inputs on the precomputed path: every point lands in the same few buckets (one run per
+    # window spans every chunk of the walk, so the whole result goes through the iterated partial
+    # merge), a half-and-half mix, and r - 1 (all digits negative after the signed recoding)
+    ksum = sum(ks) % o.R
+    same = rng.fr()
+    for chunks in (0, 3):
+        ctx.set("msm_host_chunks", chunks)
+        try:
+            assert o.g1_from_bytes(ctx.msm(big, fr_bytes([same] * n))) == o.g1_mul(o.G1_GEN, same * ksum % o.R)
+            mix = [same if i & 1 else sc[i] for i in range(n)]
+            want_mix = o.g1_mul(o.G1_GEN, sum(s * k for s, k in zip(mix, ks)) % o.R)
+            assert o.g1_from_bytes(ctx.msm(big, fr_bytes(mix))) == want_mix
+            assert o.g1_from_bytes(ctx.msm(big, fr_bytes([o.R - 1] * n))) == o.g1_mul(o.G1_GEN, (o.R - ksum) % o.R)
+        finally:
+            ctx.set("msm_host_chunks", 0)
