@@ -69,7 +69,7 @@ struct XYZZ {
     F m = xx.dbl() + xx;
     XYZZ r;
     r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * y;
+    r.y = F::mul_sub_mul(m, s - r.x, w, y);
     r.zz = v * zz;
     r.zzz = w * zzz;
     return r;
@@ -93,7 +93,7 @@ struct XYZZ {
         F xx = p.x.sqr();
         F m = xx.dbl() + xx;
         x = m.sqr() - s.dbl();
-        y = m * (s - x) - w * p.y;
+        y = F::mul_sub_mul(m, s - x, w, p.y);
         zz = v;
         zzz = w;
       } else {
@@ -104,11 +104,10 @@ struct XYZZ {
     F p2 = pp.sqr();
     F p3 = pp * p2;
     F q = x * p2;
-    F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - y * p3;
-    x = x3;
-    zz = zz * p2;
+    zz = zz * p2;            // p2 dies here, before the four-operand fused product below
     zzz = zzz * p3;
+    x = r.sqr() - p3 - q.dbl();
+    y = F::mul_sub_mul(r, q - x, y, p3);
   }
 
   // full addition  this += o   [add-2008-s]
@@ -136,7 +135,7 @@ struct XYZZ {
     F p3 = pp * p2;
     F q = u1 * p2;
     F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - s1 * p3;
+    y = F::mul_sub_mul(r, q - x3, s1, p3);
     x = x3;
     zz = zz * o.zz * p2;
     zzz = zzz * o.zzz * p3;

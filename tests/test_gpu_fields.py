@@ -8,7 +8,9 @@ pytestmark = pytest.mark.gpu
 
 OPS = {0: lambda a, b, p: (a + b) % p, 1: lambda a, b, p: (a - b) % p, 2: lambda a, b, p: a * b % p,
        3: lambda a, b, p: a * a % p, 4: lambda a, b, p: pow(a, p - 2, p), 5: lambda a, b, p: (-a) % p,
-       6: lambda a, b, p: a * a % p}
+       6: lambda a, b, p: a * a % p,
+       # fused dual products (mont_mul2: two products, one Montgomery reduction)
+       7: lambda a, b, p: (a * b + (a + b) * (a - b)) % p, 8: lambda a, b, p: (a * b - (a + b) * (a - b)) % p}
 
 
 @pytest.mark.parametrize("field", [0, 1])
