@@ -305,6 +305,9 @@ def main():
     c = bases.window or (16 if log_n >= 22 else max(4, log_n - 6))
     nwin = (255 + c - 1) // c
     imads = n * nwin * 10 * 136                       # madds * 10 modmul * 136 wide IMAD
+    # what the kernel executes per mixed addition since Y3 = R(Q - X3) - Y1 PPP shares one Montgomery
+    # reduction between its two products (mont_mul2, csrc/ff.cuh): 8 x 136 + 200 wide IMAD
+    imads_executed = n * nwin * (8 * 136 + 200)
     achieved = imads / (stage["accumulate_l1"] * 1e-3)
     hbm_peak, hbm_src = _peaks()
     roofline = {
@@ -313,7 +316,9 @@ def main():
         "frac": achieved / pipe["imad_wide_per_s"],
         "traffic": L1_TRAFFIC_BYTES_NCU if (log_n == LOG_N and bases.window == 22) else None,
         "peak_source": "measured live by zkb_bench_int_pipe (IMAD.WIDE.U32 carry chains); MEASURED_PEAKS.json has no integer-pipe peak",
-        "algorithmic_ops_per_launch": imads, "window_bits": c, "windows": nwin,
+        "algorithmic_ops_per_launch": imads, "executed_ops_per_launch": imads_executed,
+        "frac_executed": imads_executed / (stage["accumulate_l1"] * 1e-3) / pipe["imad_wide_per_s"],
+        "window_bits": c, "windows": nwin,
         "kernel_ms": stage["accumulate_l1"], "stage_ms": stage,
         "whole_msm_frac": imads / (ms_total / args.steps * 1e-3) / pipe["imad_wide_per_s"],
     }
