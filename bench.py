@@ -28,8 +28,8 @@ LOG_N = 24
 SEED = 0x5EED0000
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of msm_accumulate_l1_kernel<Fq> at the
 # default workload (2^24 points, c = 22, uniform scalars), from the `ncu --set full` capture
-# summarised in profiles/r01_SUMMARY.md (profiles/r01_ncu_full_msm_accumulate_l1_final_raw.csv)
-L1_TRAFFIC_BYTES_NCU = 28557204600   # 28.27 GB read + 0.28 GB written; algorithmic 14.5 GB
+# summarised in profiles/r01_SUMMARY.md (profiles/r01_ncu_full_msm_accumulate_l1_fused_raw.csv)
+L1_TRAFFIC_BYTES_NCU = 28517900176   # 28.23 GB read + 0.28 GB written; algorithmic 14.5 GB
 CPU_SAMPLE_LOG = 20
 
 
