@@ -88,3 +88,31 @@ def test_malformed_files_are_rejected(cio, zkb):
     # unknown section types are skipped (snarkjs adds custom-gate sections 4 and 5 to newer files)
     extra = good[:8] + struct.pack("<I", 4) + good[12:] + struct.pack("<IQ", 4, 3) + b"abc"
     assert cio.read_r1cs(extra).n_constraints == 5
+
+
+def test_parsers_survive_mutated_files(cio, zkb):
+    """truncations, byte flips, insertions and hostile 64-bit lengths: accepted or ZKB_EINVAL, never a crash."""
+    import random
+    cs, z = small_circuit(9)
+    files = [cio.write_r1cs(cs["m"], 1, 0, 2, list(zip(cs["A"], cs["B"], cs["C"]))), cio.write_wtns(z)]
+    rng = random.Random(1)
+    rejected = 0
+    for it in range(4000):
+        b = bytearray(files[it & 1])
+        kind = rng.randrange(4)
+        if kind == 0:
+            b = b[:rng.randrange(len(b) + 1)]
+        elif kind == 1:
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        elif kind == 2:
+            i = rng.randrange(len(b))
+            b[i:i] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 9)))
+        else:
+            i = rng.randrange(len(b) - 8)
+            b[i:i + 8] = rng.choice([0, 2**32 - 1, 2**64 - 1, 2**63, len(b), len(b) - i]).to_bytes(8, "little")
+        try:
+            (cio.read_wtns if it & 1 else cio.read_r1cs)(bytes(b))
+        except zkb.ZkbError:
+            rejected += 1
+    assert rejected > 1000
