@@ -26,11 +26,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 LOG_N = 24
 SEED = 0x5EED0000
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of msm_accumulate_l1_kernel<Fq> at the
-# default workload (2^24 points, c = 22, uniform scalars), from the `ncu --set full` capture
-# summarised in profiles/r01_SUMMARY.md (profiles/r01_ncu_full_msm_accumulate_l1_fused_raw.csv)
-L1_TRAFFIC_BYTES_NCU = 28517900176   # 28.23 GB read + 0.28 GB written; algorithmic 14.5 GB
-CPU_SAMPLE_LOG = 20
+CPU_SAMPLE_LOG = 22      # cpu_baseline leg of the GPU arm: one bounded 2^22-point sample
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+
+
+def _traffic(kernel, log_n, window):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, read from the
+    committed summary of the latest `ncu --set full` capture (profiles/traffic.json names the capture
+    file and the commit it was taken at); None when no capture matches this workload."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            for row in json.load(f)["captures"]:
+                if row["kernel"] == kernel and row["log_n"] == log_n and row["window_bits"] == window:
+                    return int(row["dram_bytes_read"]) + int(row["dram_bytes_write"]), row["source"]
+    except Exception:
+        pass
+    return None, None
 
 
 def _peaks():
@@ -113,10 +124,29 @@ def uniform_fr_scalars(n, seed):
         out[bad] = fresh
 
 
-def cpu_baseline_msm(sample_log=CPU_SAMPLE_LOG, reps=1):
-    """oracle B (arkworks-style VariableBaseMSM restatement) on all host threads; bounded sample."""
+def workload_config(log_n, world):
+    """the workload both arms are timed on (identical dict in the GPU line and the reference line)"""
+    return {"workload": "G1 MSM, 2^%d points per GPU, uniform scalars in [0, r), bases k_i*G (BASELINE.json configs[1])" % log_n,
+            "points_per_step_per_gpu": 1 << log_n, "global_points": world << log_n,
+            "sharding": "point range per rank + all-gather of one 64 B partial",
+            "l2": "inputs (512 MiB scalars + 1 GiB bases per rank at 2^24) larger than the 126 MB L2"}
+
+
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_b as ob
+    ob.set_threads(0)        # every host core, whatever OMP_NUM_THREADS says (torchrun exports 1)
+    return ob
+
+
+def closed_form_g1(ob, scalars_ptr, n, bases_seed):
+    """(sum s_i k_i mod r) as 32 bytes for the synthetic bases of `bases_seed`: the checker of a timed MSM"""
+    return ob.fr_dot(scalars_ptr, ob.random_scalars(n, bases_seed), n)
+
+
+def cpu_baseline_msm(sample_log=CPU_SAMPLE_LOG, reps=1):
+    """oracle B (arkworks-style VariableBaseMSM restatement) on all host threads; bounded sample."""
+    ob = _oracle()
     n = 1 << sample_log
     bases = ob.synthetic_bases(n, SEED + 1)
     scalars = ob.random_scalars(n, SEED + sample_log)
@@ -124,40 +154,46 @@ def cpu_baseline_msm(sample_log=CPU_SAMPLE_LOG, reps=1):
     for _ in range(reps):
         out, t = ob.msm_g1(bases, scalars)
         best = t if best is None else min(best, t)
+    ok = out == ob.msm_closed_form(scalars, n, SEED + 1)
     return {"value": n / best / 1e6, "unit": "Mpts/s", "cores": ob.threads(), "kind": "port",
-            "sample": "2^%d-point G1 MSM, uniform scalars, same generator as the GPU run (%.2f s)" % (sample_log, best)}, out
+            "sample": "one 2^%d-point G1 MSM, uniform scalars, bases k_i*G (%.2f s; result checked against the closed form: %s)" % (sample_log, best, ok)}
 
 
 def run_reference(args):
+    """the reference arm: oracle B's arkworks-style Pippenger on every host core, on the SAME
+    workload as the GPU arm (2^log_n uniform scalars, bases k_i*G), one full MSM per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_b as ob
-    n = 1 << CPU_SAMPLE_LOG
+    ob = _oracle()
+    log_n = args.log_n
+    n = 1 << log_n
+    t_setup = time.perf_counter()
     bases = ob.synthetic_bases(n, SEED + 1)
-    scalars = ob.random_scalars(n, SEED + CPU_SAMPLE_LOG)
+    scalars = ob.random_scalars(n, SEED + log_n)
+    t_setup = time.perf_counter() - t_setup
     for _ in range(args.warmup):
         ob.msm_g1(bases, scalars)
     t0 = time.perf_counter()
     inner = 0.0
     for _ in range(args.steps):
-        _, t = ob.msm_g1(bases, scalars)
+        out, t = ob.msm_g1(bases, scalars)
         inner += t
     wall = time.perf_counter() - t0
+    verified = out == ob.msm_closed_form(scalars, n, SEED + 1)
     value = n * args.steps / inner / 1e6
-    sample = "each step: one 2^%d-point G1 MSM (bounded sample of the 2^%d workload), %d host threads" % (
-        CPU_SAMPLE_LOG, LOG_N, ob.threads())
+    sample = "each step: one full 2^%d-point G1 MSM (the GPU arm's per-GPU workload), %d host threads" % (log_n, ob.threads())
     _emit({
         "impl": "reference", "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * inner / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)",
-        "data": "synthetic",
-        "config": {"workload": "G1 MSM, 2^%d points per GPU (BASELINE.json configs[1])" % LOG_N, "sample": sample},
+        "data": "synthetic", "config": workload_config(log_n, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": ob.threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": wall,
+        "verified": bool(verified), "wall_s": wall, "setup_s": t_setup,
     })
+    if not verified:
+        sys.exit(3)
 
 
 _JSON_OUT = None
@@ -228,7 +264,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- inputs: this rank's shard of the bases and scalars
-    bases = ctx.synthetic_bases(n, SEED + 1 + 1000 * rank)
+    bases_seed = SEED + 1 + 1000 * rank
+    bases = ctx.synthetic_bases(n, bases_seed)
     if not args.classic:
         # proving-key bases are fixed: expand them once to their window multiples in HBM
         bases.precompute(0)
@@ -254,6 +291,22 @@ def main():
             res = bytes(total.cpu().numpy())
         return res
 
+    # ---- the checker of everything timed below: (sum s_i k_i mod r) * G for this rank's shard and,
+    #      summed over the ranks, for the whole MSM (oracle B: one dot product over Fr + one scalar
+    #      multiplication; it never produces the measured result)
+    ob = _oracle()
+    dot_rank = closed_form_g1(ob, sc_host.data_ptr(), n, bases_seed)
+    want_rank = ob.g1_mul_gen(dot_rank)
+    if world > 1:
+        dots = torch.zeros(world * 32, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(dots, torch.frombuffer(bytearray(dot_rank), dtype=torch.uint8).to(dev))
+        dots = bytes(dots.cpu().numpy())
+        dsum = sum(int.from_bytes(dots[32 * g:32 * g + 32], "little") for g in range(world)) % R_MOD
+        want_total = ob.g1_mul_gen(dsum.to_bytes(32, "little"))
+    else:
+        want_total = want_rank
+    verified = {}
+
     # ---- value: device-resident
     for _ in range(args.warmup):
         step_device()
@@ -273,6 +326,9 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = ctx.launches - launches0
+    verified["device_partial"] = bytes(part.cpu().numpy()) == want_rank
+    if world > 1:
+        verified["device_total"] = bytes(total.cpu().numpy()) == want_total
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -290,6 +346,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(te.item()) / 1e6
+    verified["e2e"] = res_e2e == want_total
 
     # ---- roofline of the dominant kernel (level-1 bucket accumulation), timed live with CUDA events
     ctx.set("msm_profile", 1)
@@ -310,11 +367,12 @@ def main():
     imads_executed = n * nwin * (8 * 136 + 200)
     achieved = imads / (stage["accumulate_l1"] * 1e-3)
     hbm_peak, hbm_src = _peaks()
+    traffic, traffic_src = _traffic("msm_accumulate_l1_kernel<Fq>", log_n, bases.window)
     roofline = {
         "bound": "int_pipe", "kernel": "msm_accumulate_l1_kernel<Fq>", "achieved": achieved / 1e12,
         "peak": pipe["imad_wide_per_s"] / 1e12, "unit": "T IMAD.WIDE.U32/s",
         "frac": achieved / pipe["imad_wide_per_s"],
-        "traffic": L1_TRAFFIC_BYTES_NCU if (log_n == LOG_N and bases.window == 22) else None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "measured live by zkb_bench_int_pipe (IMAD.WIDE.U32 carry chains); MEASURED_PEAKS.json has no integer-pipe peak",
         "algorithmic_ops_per_launch": imads, "executed_ops_per_launch": imads_executed,
         "frac_executed": imads_executed / (stage["accumulate_l1"] * 1e-3) / pipe["imad_wide_per_s"],
@@ -333,12 +391,11 @@ def main():
         "metric": "g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": "G1 MSM, 2^%d points per GPU (BASELINE.json configs[1])" % log_n,
-                   "global_points": world * n, "sharding": "point range per rank + all-gather of one 64 B partial",
-                   "window_bits": c,
-                   "bases": ("window multiples 2^(c*w)*P precomputed once in HBM: %d copies, %.1f GiB per rank" % (nwin, nwin * n * 64 / 2**30))
-                   if bases.window else "plain affine bases, one bucket set per window", "l2": "inputs (512 MiB scalars + 1 GiB bases per rank) larger than the 126 MB L2",
-                   "timing": "CUDA events on the library stream, max over ranks"},
+        "config": workload_config(log_n, world),
+        "impl_detail": {"window_bits": c,
+                        "bases": ("window multiples 2^(c*w)*P precomputed once in HBM: %d copies, %.1f GiB per rank" % (nwin, nwin * n * 64 / 2**30))
+                        if bases.window else "plain affine bases, one bucket set per window",
+                        "timing": "CUDA events on the library stream, max over ranks"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 64},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "wall_s": wall,
@@ -384,8 +441,7 @@ def main():
             pk.free()
         except Exception as ex:  # never lose the primary line
             line["groth16_2^22"] = {"error": str(ex)}
-        cpu, cpu_out = cpu_baseline_msm()
-        line["cpu_baseline"] = cpu
+        line["cpu_baseline"] = cpu_baseline_msm()
     elif not args.no_extras and world > 1:
         # ---- multi-GPU extras: four-step NTT (NCCL all-to-all) and Groth16 2^22 with the witness
         #      map distributed and every MSM sharded by points
@@ -438,10 +494,18 @@ def main():
         line["cpu_baseline"] = None
     elif rank == 0:
         line["cpu_baseline"] = None
+    # every rank's checks must hold: a timed result that differs from the closed form is not a result
+    ok = torch.tensor([int(all(verified.values()))], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    line["verified"] = bool(ok.item())
+    line["verified_detail"] = {"rank0": verified, "method": "closed form (sum s_i k_i mod r)*G via oracle B, every rank, value and e2e paths"}
     if rank == 0:
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not ok.item():
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -583,6 +583,26 @@ int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g
   return ZKB_OK;
 }
 
+// canonical affine bytes already in b->d_pts -> Montgomery, with the on-curve check; synchronises
+int bases_to_mont_checked(zkb_ctx* ctx, zkb_bases* b) {
+  ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
+  ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
+  uint32_t bcoef[16];
+  host_curve_b(b->is_g2, bcoef);
+  if (b->is_g2) msm_bases_to_mont_g2(b->d_pts, b->n, bcoef, (uint32_t*)ctx->msm.flag.p, ctx->stream);
+  else msm_bases_to_mont_g1(b->d_pts, b->n, bcoef, (uint32_t*)ctx->msm.flag.p, ctx->stream);
+  uint32_t flag = 0;
+  ZKB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZKB_CUDA(ctx, cudaGetLastError());
+  if (flag & 2u) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
+    return set_error(ctx, ZKB_EINVAL, b->is_g2 ? "a G2 base is not on the twist y^2 = x^3 + 3/(9+u)"
+                                               : "a G1 base is not on the curve y^2 = x^3 + 3");
+  }
+  return ZKB_OK;
+}
+
 int bases_precompute_nolock(zkb_ctx* ctx, zkb_bases* b, int c) {
   if (!b || b->device != ctx->device) return set_error(ctx, ZKB_EINVAL, "bases belong to another device");
   if (b->precomp_c) return set_error(ctx, ZKB_EINVAL, "bases already carry precomputed multiples");
@@ -740,6 +760,27 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
 
 const char* zkb_last_error(const zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* zkb_ctx_stream(zkb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// page-locked host staging (witness / scalar buffers the host fills and the library copies from)
+int zkb_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return ZKB_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return ZKB_ENOGPU;
+  }
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return e == cudaErrorMemoryAllocation ? ZKB_ENOMEM : ZKB_ECUDA;
+  }
+  return ZKB_OK;
+}
+void zkb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 
 int zkb_ctx_sync(zkb_ctx* ctx) {
   if (!ctx) return ZKB_EINVAL;
@@ -915,14 +956,13 @@ static int bases_upload(zkb_ctx* ctx, const uint8_t* affine, uint64_t n, int is_
   int rc = bases_alloc(ctx, n, is_g2, &b);
   if (rc) return rc;
   cudaError_t e = cudaMemcpyAsync(b->d_pts, affine, n * sz, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) {
-    if (is_g2) msm_bases_to_mont_g2(b->d_pts, n, ctx->stream);
-    else msm_bases_to_mont_g1(b->d_pts, n, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
-  }
   if (e != cudaSuccess) {
     zkb_bases_free(b);
     return cuda_fail(ctx, e, "bases upload");
+  }
+  if ((rc = bases_to_mont_checked(ctx, b))) {
+    zkb_bases_free(b);
+    return rc;
   }
   *out = b;
   return ZKB_OK;

@@ -128,6 +128,7 @@ int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* 
 int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
                   uint64_t n, void* d_out_affine);
 int bases_precompute_nolock(zkb_ctx* ctx, zkb_bases* b, int c);
+int bases_to_mont_checked(zkb_ctx* ctx, zkb_bases* b);
 int bases_from_scalars(zkb_ctx* ctx, const void* d_scalars, uint64_t n, int is_g2, void* d_out);
 int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint64_t count,
                           uint8_t* out);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <array>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <new>
@@ -43,7 +44,19 @@ struct zkb_pk {
   uint32_t rank = 0, world = 1;
   uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (dist_ntt.py)
   uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
+  // the prove entry points write the key's work vectors (d_a..d_zm, d_results, d_proof) behind a
+  // const zkb_pk*: one prove at a time per key, whatever context it is called through
+  mutable std::atomic_flag busy = ATOMIC_FLAG_INIT;
 };
+
+namespace zkb {
+struct PkGuard {
+  const zkb_pk* pk;
+  bool ok;
+  explicit PkGuard(const zkb_pk* k) : pk(k), ok(k && !k->busy.test_and_set()) {}
+  ~PkGuard() { if (ok) pk->busy.clear(); }
+};
+}  // namespace zkb
 
 namespace zkb {
 
@@ -309,6 +322,9 @@ void zkb_pk_free(zkb_pk* pk) {
   delete pk;
 }
 
+uint64_t zkb_pk_n_vars(const zkb_pk* pk) { return pk ? pk->m : 0; }
+uint32_t zkb_pk_log_n(const zkb_pk* pk) { return pk ? pk->log_n : 0; }
+
 const zkb_bases* zkb_pk_query(const zkb_pk* pk, int which) {
   if (!pk) return nullptr;
   switch (which) {
@@ -557,10 +573,12 @@ static int bases_from_bytes(zkb_ctx* ctx, const uint8_t* pts, uint64_t count, ui
   *out = b;
   ZKB_CUDA(ctx, cudaMemsetAsync(b->d_pts, 0, pad_front * sz, ctx->stream));
   ZKB_CUDA(ctx, cudaMemcpyAsync((char*)b->d_pts + pad_front * sz, pts, count * sz, cudaMemcpyHostToDevice, ctx->stream));
-  if (is_g2) msm_bases_to_mont_g2(b->d_pts, b->n, ctx->stream);
-  else msm_bases_to_mont_g1(b->d_pts, b->n, ctx->stream);
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
+  int rc = bases_to_mont_checked(ctx, b);
+  if (rc) {
+    zkb_bases_free(b);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 extern "C" {
@@ -823,6 +841,8 @@ static int prove_msm_only_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
   if (!(pk)) return set_error(ctx, ZKB_EINVAL, "null proving key");                       \
   if ((pk)->device != (ctx)->device)                                                      \
     return set_error(ctx, ZKB_EINVAL, "proving key lives on another device");            \
+  PkGuard pk_guard(pk);                                                                   \
+  if (!pk_guard.ok) return set_error(ctx, ZKB_EBUSY, "proving key is in use by another prove call"); \
   ZKB_CUDA(ctx, cudaSetDevice((ctx)->device));
 
 int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
@@ -833,6 +853,8 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, co
   if (!witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   if (pk->world != 1)
     return set_error(ctx, ZKB_EINVAL, "sharded key: use zkb_groth16_prove_partial + zkb_groth16_assemble");
+  if (pk->h_low_bits)
+    return set_error(ctx, ZKB_EINVAL, "key stores h_query in the four-step layout: use the distributed prover");
   int rc = prove_msm_phase(ctx, pk, witness, timings_opt, h_out_opt, intermediates_opt);
   if (rc) {
     std::memset(proof_out, 0, ZKB_PROOF_BYTES);
@@ -848,6 +870,8 @@ int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wit
                               uint8_t partial_out[ZKB_INTERMEDIATE_BYTES], zkb_prove_timings* timings_opt) {
   ZKB_PK_ENTER(ctx, pk);
   if (!witness || !partial_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (pk->h_low_bits)   // the single-GPU witness map leaves h in natural order: it would meet the wrong bases
+    return set_error(ctx, ZKB_EINVAL, "key stores h_query in the four-step layout: use the distributed prover");
   return prove_msm_phase(ctx, pk, witness, timings_opt, nullptr, partial_out);
 }
 

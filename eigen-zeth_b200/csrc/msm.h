@@ -70,8 +70,12 @@ void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
 void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
 void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
-void msm_bases_to_mont_g1(void* d_pts, uint64_t n, cudaStream_t s);
-void msm_bases_to_mont_g2(void* d_pts, uint64_t n, cudaStream_t s);
+// canonical affine -> Montgomery affine in place; every point that is neither the all-zero encoding
+// of infinity nor on the curve raises bit 1 of *d_flag (d_flag may be null: no check).
+// b_mont: the curve coefficient (8 / 16 Montgomery words, host pointer).
+void msm_bases_to_mont_g1(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s);
+void msm_bases_to_mont_g2(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s);
+void host_curve_b(int is_g2, uint32_t* out);
 void msm_sum_affine_g1(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s);
 void msm_sum_affine_g2(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s);
 

@@ -10,7 +10,9 @@ void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets
   msm_merge_t<Fq>(p, main_buckets, part_buckets, s);
 }
 void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) { msm_tail_t<Fq>(p, b, s); }
-void msm_bases_to_mont_g1(void* d_pts, uint64_t n, cudaStream_t s) { msm_bases_to_mont_t<Fq>(d_pts, n, s); }
+void msm_bases_to_mont_g1(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {
+  msm_bases_to_mont_t<Fq>(d_pts, n, b_mont, d_flag, s);
+}
 void msm_sum_affine_g1(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s) {
   msm_sum_affine_t<Fq>(d_pts, n, d_out, s);
 }

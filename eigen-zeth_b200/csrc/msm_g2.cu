@@ -10,7 +10,9 @@ void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets
   msm_merge_t<Fq2>(p, main_buckets, part_buckets, s);
 }
 void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) { msm_tail_t<Fq2>(p, b, s); }
-void msm_bases_to_mont_g2(void* d_pts, uint64_t n, cudaStream_t s) { msm_bases_to_mont_t<Fq2>(d_pts, n, s); }
+void msm_bases_to_mont_g2(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {
+  msm_bases_to_mont_t<Fq2>(d_pts, n, b_mont, d_flag, s);
+}
 void msm_sum_affine_g2(const void* d_pts, uint32_t n, void* d_out, cudaStream_t s) {
   msm_sum_affine_t<Fq2>(d_pts, n, d_out, s);
 }

@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "ec.cuh"
 #include "msm.h"
 
@@ -254,14 +256,19 @@ __global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ wl, const XYZZ<F>*
 }
 
 // ---------------------------------------------------------------- base upload / point utilities
-// canonical affine -> Montgomery affine (infinity = all zero stays all zero)
+// canonical affine -> Montgomery affine (infinity = all zero stays all zero); points that are not on
+// y^2 = x^3 + b raise bit 1 of *flag (an off-curve point of small even order would break the
+// "a base never doubles to infinity" assumption of msm_precompute_kernel and silently zero its
+// window multiples)
 template <class F>
-__global__ void msm_bases_to_mont_kernel(Affine<F>* pts, uint64_t n) {
+__global__ void msm_bases_to_mont_kernel(Affine<F>* pts, uint64_t n, F b, uint32_t* flag) {
   uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   Affine<F> p = Affine<F>::load(pts + i);
+  const bool inf = p.is_inf();
   p.x = p.x.to_mont();
   p.y = p.y.to_mont();
+  if (flag && !inf && !(p.y.sqr() == p.x.sqr() * p.x + b)) atomicOr(flag, 2u);
   p.store(pts + i);
 }
 
@@ -435,10 +442,14 @@ void msm_precompute_t(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, 
 }
 
 template <class F>
-void msm_bases_to_mont_t(void* d_pts, uint64_t n, cudaStream_t s) {
+void msm_bases_to_mont_t(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {
   uint32_t blocks = uint32_t((n + 127) / 128);
   if (blocks) {
-    msm_bases_to_mont_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<Affine<F>*>(d_pts), n);
+    F b;
+    static_assert(sizeof(F) % 4 == 0, "field element is a whole number of words");
+    if (b_mont) memcpy(&b, b_mont, sizeof(F)); else memset(&b, 0, sizeof(F));
+    msm_bases_to_mont_kernel<F><<<blocks, 128, 0, s>>>(reinterpret_cast<Affine<F>*>(d_pts), n, b,
+                                                       b_mont ? d_flag : nullptr);
     count_launches(1);
   }
 }

@@ -109,6 +109,22 @@ F2 twist_b() {
   return F2{B1, HFq::zero()} * xi.inverse();
 }
 
+}  // namespace
+namespace zkb {
+// curve coefficient b in Montgomery form as 32-bit words: 8 words for G1 (b = 3), 16 for the twist
+// (b' = 3 / (9 + u), c0 then c1) — used by the on-curve check of uploaded bases (msm_impl.cuh)
+void host_curve_b(int is_g2, uint32_t* out) {
+  if (!is_g2) {
+    std::memcpy(out, B1.l, 32);
+  } else {
+    F2 b = twist_b();
+    std::memcpy(out, b.a.l, 32);
+    std::memcpy(out + 8, b.b.l, 32);
+  }
+}
+}  // namespace zkb
+namespace {
+
 bool g1_on_curve(const G1& p) { return p.inf || p.y.sqr() == p.x.sqr() * p.x + B1; }
 bool g2_on_curve(const G2& p) { return p.inf || p.y.sqr() == p.x.sqr() * p.x + twist_b(); }
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_proof_check",
     "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
-    "zkb_ctx_launches", "zkb_msm_last_timings",
+    "zkb_ctx_launches", "zkb_msm_last_timings", "zkb_host_alloc", "zkb_host_free", "zkb_pk_n_vars", "zkb_pk_log_n",
 ]
 
 
@@ -82,6 +82,9 @@ def load_library() -> C.CDLL:
     lib.zkb_ctx_stream.restype = vp
     lib.zkb_ctx_sync.argtypes = [vp]
     lib.zkb_ctx_set.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.zkb_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    lib.zkb_host_free.argtypes = [vp]
+    lib.zkb_host_free.restype = None
     lib.zkb_fr_ntt.argtypes = [vp, vp, u32, i32, i32]
     lib.zkb_fr_ntt_dev.argtypes = [vp, vp, vp, u32, i32, i32, i32]
     lib.zkb_fr_ntt_batch_dev.argtypes = [vp, vp, vp, u32, u64, i32, i32, vp, vp]
@@ -119,6 +122,10 @@ def load_library() -> C.CDLL:
         lib.zkb_pk_free.restype = None
         lib.zkb_pk_query.argtypes = [vp, i32]
         lib.zkb_pk_query.restype = vp
+        lib.zkb_pk_n_vars.argtypes = [vp]
+        lib.zkb_pk_n_vars.restype = u64
+        lib.zkb_pk_log_n.argtypes = [vp]
+        lib.zkb_pk_log_n.restype = u32
         lib.zkb_synthetic_witness.argtypes = [u32, u8p, u8p, vp]
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
@@ -189,6 +196,18 @@ class BorrowedBases(Bases):
 class ProvingKey:
     def __init__(self, ctx, handle, vk: bytes, log_n: int):
         self.ctx, self.handle, self.vk, self.log_n = ctx, handle, vk, log_n
+        self.n_vars = int(ctx.lib.zkb_pk_n_vars(handle))
+
+    def witness_ptr(self, witness):
+        """bytes (length-checked against the key: the C ABI takes a bare pointer and would read
+        32 * n_vars bytes whatever it is given) or a raw host / device address (the caller's promise)."""
+        if isinstance(witness, (bytes, bytearray)):
+            if len(witness) != 32 * self.n_vars:
+                raise ValueError("witness holds %d bytes, the key has %d variables (%d bytes)"
+                                 % (len(witness), self.n_vars, 32 * self.n_vars))
+            buf = C.create_string_buffer(bytes(witness), len(witness))
+            return C.cast(buf, C.c_void_p), buf
+        return C.c_void_p(int(witness)), None
 
     def query(self, which: int) -> "Bases":
         """borrowed view of a query (0 a, 1 b_g1, 2 b_g2, 3 l, 4 h)."""
@@ -351,6 +370,21 @@ class Context:
         d = PkDesc()
         d.log_n, d.n_public, d.n_vars = log_n, n_public, n_vars
         d.n_constraints = len(matrices[0][0]) - 1
+        # the C ABI takes bare pointers: every array length is checked here against the dimensions
+        n = 1 << log_n
+        want = {"a_query": 64 * n_vars, "b_g1_query": 64 * n_vars, "b_g2_query": 128 * n_vars,
+                "l_query": 64 * max(n_vars - n_public - 1, 0), "h_query": 64 * (n - 1)}
+        for name, size in want.items():
+            if len(queries[name]) != size:
+                raise ValueError("%s holds %d bytes, expected %d" % (name, len(queries[name]), size))
+        for name, size in (("alpha_g1", 64), ("beta_g1", 64), ("delta_g1", 64), ("beta_g2", 128), ("delta_g2", 128)):
+            if len(fixed[name]) != size:
+                raise ValueError("%s must be %d bytes" % (name, size))
+        for k, (rp, col, coeff) in enumerate(matrices):
+            if len(rp) != d.n_constraints + 1:
+                raise ValueError("matrix %d: row_ptr needs n_constraints + 1 entries" % k)
+            if len(col) != rp[-1] or len(coeff) != 32 * rp[-1]:
+                raise ValueError("matrix %d: col / coeff lengths do not match row_ptr[-1] = %d" % (k, rp[-1]))
         keep = []
         for k, (rp, col, coeff) in enumerate(matrices):
             a_rp, a_col = array.array("I", rp), array.array("I", col)
@@ -374,22 +408,14 @@ class Context:
     def groth16_witness_dev(self, pk: ProvingKey, witness):
         """H2D + R1CS products; returns the device pointers of the a, b, c evaluation vectors."""
         ptrs = (C.c_void_p * 3)()
-        if isinstance(witness, (bytes, bytearray)):
-            wbuf = C.create_string_buffer(bytes(witness), len(witness))
-            wptr = C.cast(wbuf, C.c_void_p)
-        else:
-            wptr = C.c_void_p(int(witness))
+        wptr, _keep = pk.witness_ptr(witness)
         self._check(self.lib.zkb_groth16_witness_dev(self.h, pk.handle, wptr, ptrs))
         return [int(p) for p in ptrs]
 
     def groth16_witness_layout_dev(self, pk: ProvingKey, witness, low_bits: int, world: int, rank: int, d_abc):
         """R1CS products for this rank's layout-d rows only, written into the three given buffers."""
         ptrs = (C.c_void_p * 3)(*[int(p) for p in d_abc])
-        if isinstance(witness, (bytes, bytearray)):
-            wbuf = C.create_string_buffer(bytes(witness), len(witness))
-            wptr = C.cast(wbuf, C.c_void_p)
-        else:
-            wptr = C.c_void_p(int(witness))
+        wptr, _keep = pk.witness_ptr(witness)
         self._check(self.lib.zkb_groth16_witness_layout_dev(self.h, pk.handle, wptr, low_bits, world, rank, ptrs))
 
     def groth16_msm_dev(self, pk: ProvingKey, d_h: int) -> bytes:
@@ -404,11 +430,7 @@ class Context:
         """-> (384-byte partial MSM sums over this key's point ranges, timings)"""
         out = C.create_string_buffer(INTERMEDIATE_BYTES)
         t = ProveTimings()
-        if isinstance(witness, (bytes, bytearray)):
-            wbuf = C.create_string_buffer(bytes(witness), len(witness))
-            wptr = C.cast(wbuf, C.c_void_p)
-        else:
-            wptr = C.c_void_p(int(witness))
+        wptr, _keep = pk.witness_ptr(witness)
         self._check(self.lib.zkb_groth16_prove_partial(self.h, pk.handle, wptr, out, C.byref(t)))
         return out.raw, t.as_dict()
 
@@ -423,11 +445,7 @@ class Context:
         inter = C.create_string_buffer(INTERMEDIATE_BYTES) if want_intermediates else None
         hbuf = C.create_string_buffer(32 * ((1 << pk.log_n) - 1)) if want_h else None
         t = ProveTimings()
-        if isinstance(witness, (bytes, bytearray)):
-            wbuf = C.create_string_buffer(bytes(witness), len(witness))
-            wptr = C.cast(wbuf, C.c_void_p)
-        else:
-            wptr = C.c_void_p(int(witness))
+        wptr, _keep = pk.witness_ptr(witness)
         self._check(self.lib.zkb_groth16_prove(self.h, pk.handle, wptr, r, s, proof, inter, hbuf, C.byref(t)))
         return proof.raw, (inter.raw if inter else None), (hbuf.raw if hbuf else None), t.as_dict()
 
@@ -451,6 +469,27 @@ class Context:
         return {"imad_wide_per_s": res[0], "montmul_per_s": res[1], "sm_mhz": res[2]}
 
 
+def host_alloc(nbytes: int) -> int:
+    """page-locked host memory (zkb_host_alloc) -> address"""
+    p = C.c_void_p()
+    rc = load_library().zkb_host_alloc(nbytes, C.byref(p))
+    if rc:
+        raise ZkbError(rc, "zkb_host_alloc(%d) failed" % nbytes)
+    return int(p.value)
+
+
+def host_free(ptr: int):
+    load_library().zkb_host_free(C.c_void_p(ptr))
+
+
+def host_read(ptr: int, nbytes: int) -> bytes:
+    return C.string_at(ptr, nbytes)
+
+
+def host_write(ptr: int, data: bytes):
+    C.memmove(ptr, bytes(data), len(data))
+
+
 def fr_root_of_unity(log_n: int, inverse=False) -> bytes:
     out = C.create_string_buffer(32)
     load_library().zkb_fr_root_of_unity(log_n, int(inverse), out)
@@ -464,6 +503,13 @@ def synthetic_witness(log_n: int, w0: bytes, w1: bytes) -> bytes:
     if rc:
         raise ZkbError(rc, "zkb_synthetic_witness failed")
     return out.raw
+
+
+def synthetic_witness_into(log_n: int, w0: bytes, w1: bytes, ptr: int):
+    """as synthetic_witness, written straight into caller memory (e.g. a zkb_host_alloc buffer)"""
+    rc = load_library().zkb_synthetic_witness(log_n, w0, w1, C.c_void_p(ptr))
+    if rc:
+        raise ZkbError(rc, "zkb_synthetic_witness failed")
 
 
 def groth16_verify(vk: bytes, proof: bytes, public_input: bytes) -> bool:

@@ -166,3 +166,45 @@ class ProofResult:
         d = json.loads(s)
         return ProofResult(int(d["block_number"]), d["proof"], d["public_input"], bytes(d["pre_state_root"]),
                            bytes(d["post_state_root"]))
+
+
+PREFIX_BATCH_PROOF = "BATCH_PROOF_"          # src/db/mod.rs:42-45
+
+
+def batch_proof_key(block_no: int) -> bytes:
+    """the rollup-DB key a finished proof is stored under (src/settlement/worker.rs:179-182) and
+    looked up by (src/custom_reth/eigen.rs:77-82)."""
+    return (PREFIX_BATCH_PROOF + str(int(block_no))).encode()
+
+
+@dataclass
+class BatchProofInfo:
+    """The `eigenrpc_getBatchProof` view of a stored ProofResult (src/custom_reth/eigen.rs:76-97,
+    struct at :108-117): proof / public_input verbatim, state roots as "0x" + lower-case hex."""
+    block_number: int
+    proof: str
+    public_input: str
+    pre_state_root: str
+    post_state_root: str
+
+    def to_json(self) -> str:
+        return json.dumps({"block_number": self.block_number, "proof": self.proof, "public_input": self.public_input,
+                           "pre_state_root": self.pre_state_root, "post_state_root": self.post_state_root})
+
+
+def get_batch_proof(db_get, block_no: int):
+    """eigenrpc_getBatchProof over any `db_get(key: bytes) -> bytes | None` (the reference's
+    Database::get, src/db/mod.rs:12-16): None when no proof is stored for the block, else the
+    BatchProofInfo the RPC returns.  A stored value that is not a ProofResult raises ValueError (the
+    reference answers with an internal RPC error, eigen.rs:84-85)."""
+    raw = db_get(batch_proof_key(block_no))
+    if raw is None:
+        return None
+    try:
+        pr = ProofResult.from_json(raw.decode() if isinstance(raw, (bytes, bytearray)) else raw)
+    except (KeyError, TypeError, json.JSONDecodeError) as ex:
+        raise ValueError("stored batch proof is not a ProofResult: %s" % ex)
+    if len(pr.pre_state_root) != 32 or len(pr.post_state_root) != 32:
+        raise ValueError("stored state roots must be 32 bytes")
+    return BatchProofInfo(pr.block_number, pr.proof, pr.public_input, "0x" + pr.pre_state_root.hex(),
+                          "0x" + pr.post_state_root.hex())

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import argparse
 import hashlib
+import hmac
 import json
 import logging
 import os
@@ -38,6 +39,7 @@ log = logging.getLogger("zkb.prover")
 R = proof_format.R
 VERSION_SERVER = "zkb-0.1.0"
 VERSION_PROTO = "v0_0_1"
+DEFAULT_AGGREGATOR = "479881985774944702531460751064278034642760119942"    # reference src/commands/run.rs:76
 
 
 def _h(*parts) -> bytes:
@@ -55,37 +57,146 @@ def _fr_from_hash(*parts) -> bytes:
     return v.to_bytes(32, "little")
 
 
-class GpuGroth16Backend:
-    """GenFinalProof on one B200.  No CPU fallback: constructing it without the CUDA library or an
-    sm_100 GPU raises."""
+def _blinding(secret: bytes, tag: str, batch_id: str, recursive_proof: str, aggregator_addr: str) -> bytes:
+    """Groth16 blinding scalar: HMAC-SHA256 under a server-side secret over EVERYTHING the proof is a
+    function of (batch id, witness source, aggregator).  Never derived from public request fields
+    alone — anyone who can recompute r, s strips the blinding (A - r*delta) and zero-knowledge is
+    gone; and one (r, s) is never reused on two different witnesses."""
+    m = hmac.new(secret, digestmod=hashlib.sha256)
+    for part in (tag, batch_id, recursive_proof, aggregator_addr):
+        b = part.encode()
+        m.update(len(b).to_bytes(8, "little"))
+        m.update(b)
+    return (int.from_bytes(m.digest(), "little") & ((1 << 253) - 1)).to_bytes(32, "little")
 
-    def __init__(self, log_n: int = 16, setup_seed: int = 0x5EED0004, device: int = 0, self_check: bool = True):
+
+def load_or_create_secret(path: str | None) -> bytes:
+    """32 random bytes; persisted (mode 0600) when a path is given so that a restarted server replays
+    a batch with the same blinding (idempotent GenFinalProof, provider.rs:245-274)."""
+    if path and os.path.exists(path):
+        with open(path, "rb") as f:
+            sec = f.read()
+        if len(sec) < 32:
+            raise ValueError("secret file %s holds fewer than 32 bytes" % path)
+        return sec
+    sec = os.urandom(32)
+    if path:
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_EXCL, 0o600)
+        with os.fdopen(fd, "wb") as f:
+            f.write(sec)
+    return sec
+
+
+class _PinnedWitness:
+    """witness staging in page-locked host memory (zkb_host_alloc): the H2D copy inside
+    zkb_groth16_prove then runs at PCIe speed instead of through a pageable bounce buffer."""
+
+    def __init__(self, lib, nbytes):
+        self.lib, self.nbytes = lib, nbytes
+        self.ptr = lib.host_alloc(nbytes)
+
+    def free(self):
+        if self.ptr:
+            self.lib.host_free(self.ptr)
+            self.ptr = 0
+
+
+class GpuGroth16Backend:
+    """GenFinalProof on the B200s named in `devices`.  No CPU fallback: constructing it without the
+    CUDA library or an sm_100 GPU raises.
+
+    The synthetic circuit's setup is TEST-ONLY: its toxic waste comes from `setup_seed`, so whoever
+    knows the seed can forge proofs for the exported verifying key.  A production deployment loads a
+    ceremony key through zkb_pk_load instead."""
+
+    def __init__(self, log_n: int = 16, setup_seed: int | None = None, device: int = 0, self_check: bool = True,
+                 secret: bytes | None = None, devices=None):
         from . import lib
         self.lib = lib
-        self.ctx = lib.Context(device)
         self.log_n = log_n
-        t0 = time.time()
-        self.pk = self.ctx.pk_synthetic(log_n, setup_seed)
         self.self_check = self_check
-        log.info("proving key for 2^%d constraints resident on GPU %d (%.1f s)", log_n, device, time.time() - t0)
+        self.secret = secret if secret is not None else os.urandom(32)
+        if setup_seed is None:                                     # never logged, never derivable
+            setup_seed = int.from_bytes(os.urandom(8), "little")
+        devices = list(devices) if devices else [device]
+        t0 = time.time()
+        if len(devices) == 1:
+            self.group = None
+            self.ctx = lib.Context(devices[0])
+            self.pk = self.ctx.pk_synthetic(log_n, setup_seed)
+            self._vk = self.pk.vk
+        else:
+            self.group = lib.DeviceGroup(devices)                   # one context + NCCL rank per GPU
+            self.group.pk_synthetic(log_n, setup_seed)
+            self._vk = self.group.vk
+        self._buf = [_PinnedWitness(lib, 32 << log_n) for _ in range(2)]
+        self._next = 0
+        self._pre = None                                           # (key, thread, buffer)
+        self._pre_lock = threading.Lock()
+        log.info("proving key for 2^%d constraints resident on GPU(s) %s (%.1f s)", log_n, devices, time.time() - t0)
 
     @property
     def vk(self) -> bytes:
-        return self.pk.vk
+        return self._vk
+
+    # ---- witness: generated ahead of the request whenever its inputs are already known
+    def _witness_seeds(self, recursive_proof, aggregator_addr):
+        return _fr_from_hash("w0", recursive_proof, aggregator_addr), _fr_from_hash("w1", recursive_proof, aggregator_addr)
+
+    def prefetch(self, recursive_proof: str, aggregator_addr: str):
+        """Start generating the witness for (recursive_proof, aggregator_addr) in the background.  The
+        servicer calls this when it hands out an aggregated proof: the client sends that very string
+        back as GenFinalProofRequest.recursive_proof one step (>= 1 s, provider.rs:542) later."""
+        key = (recursive_proof, aggregator_addr)
+        with self._pre_lock:
+            if self._pre and self._pre[0] == key:
+                return
+            buf = self._buf[self._next]
+            self._next ^= 1
+            w0, w1 = self._witness_seeds(*key)
+            th = threading.Thread(target=self.lib.synthetic_witness_into, args=(self.log_n, w0, w1, buf.ptr), daemon=True)
+            self._pre = (key, th, buf)
+            th.start()
+
+    def _witness(self, recursive_proof, aggregator_addr):
+        key = (recursive_proof, aggregator_addr)
+        with self._pre_lock:
+            pre = self._pre if self._pre and self._pre[0] == key else None
+        if pre is None:
+            self.prefetch(recursive_proof, aggregator_addr)
+            with self._pre_lock:
+                pre = self._pre
+        pre[1].join()
+        return pre[2]
 
     def final_proof(self, batch_id: str, recursive_proof: str, aggregator_addr: str):
-        w0 = _fr_from_hash("w0", recursive_proof, aggregator_addr)
-        w1 = _fr_from_hash("w1", recursive_proof, aggregator_addr)
-        r = _fr_from_hash("r", batch_id)
-        s = _fr_from_hash("s", batch_id)
-        witness = self.lib.synthetic_witness(self.log_n, w0, w1)
-        proof, _, _, timings = self.ctx.groth16_prove(self.pk, witness, r, s)
-        public_input = witness[32:64]
-        if self.self_check and not self.lib.groth16_verify(self.pk.vk, proof, public_input):
+        t = {}
+        t0 = time.perf_counter()
+        wbuf = self._witness(recursive_proof, aggregator_addr)
+        t["witness_wait_ms"] = 1e3 * (time.perf_counter() - t0)
+        r = _blinding(self.secret, "r", batch_id, recursive_proof, aggregator_addr)
+        s = _blinding(self.secret, "s", batch_id, recursive_proof, aggregator_addr)
+        t0 = time.perf_counter()
+        if self.group is None:
+            proof, _, _, dev_t = self.ctx.groth16_prove(self.pk, wbuf.ptr, r, s)
+        else:
+            proof, dev_t = self.group.groth16_prove(wbuf.ptr, r, s)
+        t["prove_call_ms"] = 1e3 * (time.perf_counter() - t0)
+        public_input = self.lib.host_read(wbuf.ptr + 32, 32)
+        t0 = time.perf_counter()
+        if self.self_check and not self.lib.groth16_verify(self._vk, proof, public_input):
             raise RuntimeError("pairing check failed on a freshly generated proof")
+        t["pairing_check_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
         proof_json, input_json = proof_format.proof_to_json(proof), proof_format.public_input_to_json(public_input)
         proof_format.validate_final_proof(proof_json, input_json)     # what leaves is what verify_batches will accept
-        return proof_json, input_json, timings
+        t["format_and_check_ms"] = 1e3 * (time.perf_counter() - t0)
+        t.update(dev_t)
+        return proof_json, input_json, t
+
+    def close(self):
+        for b in self._buf:
+            b.free()
 
 
 class BatchLedger:
@@ -147,6 +258,7 @@ class ProverServicer:
         self.current_id, self.current_start = "", 0
         self.last_id, self.last_end = "", 0
         self.timings = []
+        self.last_aggregator = DEFAULT_AGGREGATOR
 
     # ---- stubs for the out-of-scope zkVM steps (deterministic in batch_id / block numbers)
     def _gen_batch_chunks(self, req):
@@ -178,9 +290,17 @@ class ProverServicer:
 
     def _gen_aggregated(self, req):
         self.ledger.record(req.batch_id, "aggregated")
-        return pb.GenAggregatedProofResponse(
-            batch_id=req.batch_id, result_code=pb.COMPLETED_OK,
-            result_string=_h("agg", req.recursive_proof_1, req.recursive_proof_2).hex())
+        result = _h("agg", req.recursive_proof_1, req.recursive_proof_2).hex()
+        # the client sends `result` back as GenFinalProofRequest.recursive_proof after its 1 s step
+        # sleep (provider.rs:472-483, :542): start building that witness now, with the aggregator
+        # address this operator used last (it is a constant of the operator, commands/run.rs:76)
+        pre = getattr(self.backend, "prefetch", None)
+        if pre is not None and self.last_aggregator is not None:
+            try:
+                pre(result, self.last_aggregator)
+            except Exception:
+                log.exception("witness prefetch failed (the final step will generate it)")
+        return pb.GenAggregatedProofResponse(batch_id=req.batch_id, result_code=pb.COMPLETED_OK, result_string=result)
 
     # ---- the Groth16 step
     def _gen_final(self, req, request_id):
@@ -188,6 +308,7 @@ class ProverServicer:
             return pb.GenFinalProofResponse(batch_id=req.batch_id, result_code=pb.COMPLETED_ERROR,
                                             error_message="unsupported curve %r (only BN128)" % req.curve_name)
         key = (req.batch_id, req.recursive_proof, req.aggregator_addr)
+        self.last_aggregator = req.aggregator_addr
         # no consistency facts here: a re-aggregated batch may legitimately carry another recursive
         # proof, and an error would make the client resend the same request forever (provider.rs:511-516)
         self.ledger.record(req.batch_id, "final")
@@ -266,6 +387,17 @@ class ProverServicer:
                 resp.gen_final_proof.CopyFrom(pb.GenFinalProofResponse(result_code=pb.COMPLETED_ERROR, error_message=str(ex)))
             elif kind == "gen_aggregated_proof":
                 resp.gen_aggregated_proof.CopyFrom(pb.GenAggregatedProofResponse(result_code=pb.COMPLETED_ERROR, error_message=str(ex)))
+            elif kind == "gen_batch_proof":
+                # the client forwards only same-variant responses to ProverChannel (provider.rs:646-668);
+                # a GetStatus answer here would leave it blocked on response_receiver.recv() forever
+                if request.gen_batch_proof.WhichOneof("step") == "gen_chunk_proof":
+                    resp.gen_batch_proof.CopyFrom(pb.GenBatchProofResponse(gen_chunk_proof=pb.GenChunkProofResult(
+                        batch_id=request.gen_batch_proof.gen_chunk_proof.batch_id, result_code=pb.COMPLETED_ERROR,
+                        error_message=str(ex))))
+                else:
+                    resp.gen_batch_proof.CopyFrom(pb.GenBatchProofResponse(gen_batch_chunks=pb.GenBatchChunksResult(
+                        batch_id=request.gen_batch_proof.gen_batch_chunks.batch_id, result_code=pb.COMPLETED_ERROR,
+                        error_message=str(ex), pre_state_root=bytes(32), post_state_root=bytes(32))))
             else:
                 resp.get_status.CopyFrom(pb.GetStatusResponse(id=request.id, result_code=1, error_message=str(ex)))
         return resp
@@ -292,17 +424,31 @@ def main(argv=None):
     ap.add_argument("--address", default="0.0.0.0:50061")
     ap.add_argument("--log-n", type=int, default=16, help="log2 of the synthetic circuit's QAP domain")
     ap.add_argument("--device", type=int, default=0)
-    ap.add_argument("--setup-seed", type=lambda s: int(s, 0), default=0x5EED0004)
+    ap.add_argument("--devices", default=None, help="comma-separated GPU list, e.g. 0,1,2,3,4,5,6,7: one proof is "
+                    "spread over all of them (four-step NTTs + every MSM sharded by point range)")
+    ap.add_argument("--insecure-synthetic-setup", action="store_true",
+                    help="REQUIRED to serve the synthetic test circuit: its trusted setup is generated locally, "
+                         "so whoever holds the seed can forge proofs for the exported verifying key")
+    ap.add_argument("--setup-seed", type=lambda s: int(s, 0), default=None,
+                    help="reproducible (publicly known!) toxic waste for tests; default: fresh random, never logged")
+    ap.add_argument("--secret-file", default=None, help="32-byte blinding secret (created if absent, mode 0600)")
     ap.add_argument("--vk-out", default=None, help="write the verifying key (hex, include/zkb.h layout) here")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s %(message)s")
-    backend = GpuGroth16Backend(args.log_n, args.setup_seed, args.device)
+    if not args.insecure_synthetic_setup:
+        ap.error("this build serves only the synthetic test circuit, whose trusted setup is NOT a ceremony: "
+                 "pass --insecure-synthetic-setup to acknowledge that its proofs are forgeable by the key holder "
+                 "(production keys enter through zkb_pk_load, see INTEGRATION.md)")
+    log.warning("TEST-ONLY trusted setup: the synthetic circuit's toxic waste is generated on this host; "
+                "do not point a production verifier at the exported verifying key")
+    devices = [int(x) for x in args.devices.split(",")] if args.devices else [args.device]
+    backend = GpuGroth16Backend(args.log_n, args.setup_seed, devices=devices, secret=load_or_create_secret(args.secret_file))
     if args.vk_out:
         with open(args.vk_out, "w") as f:
             f.write(backend.vk.hex())
     server, port = make_server(ProverServicer(backend), args.address)
     server.start()
-    log.info("ProverService listening on %s (port %d)", args.address, port)
+    log.info("ProverService listening on %s (port %d), GPUs %s", args.address, port, devices)
     server.wait_for_termination()
 
 

@@ -13,8 +13,14 @@
  *  - G1 affine: x||y (64 B); G2 affine: x.c0||x.c1||y.c0||y.c1 (128 B); all-zero = infinity.
  *    (c0 first is the order of reference proof/proof.json "pi_b", read unswapped by
  *     src/settlement/ethereum/mod.rs:451-466.)
- *  - a zkb_ctx is bound to ONE GPU (one process per GPU; ranks are composed above this layer
- *    with NCCL) and is not re-entrant: one call at a time per ctx (ZKB_EBUSY otherwise);
+ *  - a zkb_ctx is bound to ONE GPU and is not re-entrant: one call at a time per ctx (ZKB_EBUSY
+ *    otherwise).  Several GPUs = several contexts (one per process, or one per host thread), joined
+ *    into a communicator with zkb_comm_init; the zkb_*_dist calls are then collective;
+ *  - a proving key is used by one prove call at a time (its work vectors live in the key): a second
+ *    concurrent call on the same key returns ZKB_EBUSY;
+ *  - uploaded bases / proving-key queries must be on the curve (checked on the GPU, ZKB_EINVAL
+ *    otherwise); G2 points are NOT checked for membership of the order-r subgroup (a ceremony key
+ *    is expected to have been validated by its own tooling);
  *  - `*_dev` variants take raw device pointers on the ctx's device and enqueue on the ctx's
  *    stream (zkb_ctx_stream) without synchronising, so callers can time them with CUDA events.
  */
@@ -35,6 +41,7 @@ extern "C" {
 #define ZKB_EBUSY (-4)    /* ctx already executing a call on another thread */
 #define ZKB_ENOGPU (-5)   /* no usable sm_100 device: there is no CPU fallback */
 #define ZKB_EVERIFY (-6)  /* pairing check failed */
+#define ZKB_ECOMM (-7)    /* NCCL / peer-memory failure in a multi-GPU call (message in zkb_last_error) */
 
 typedef struct zkb_ctx zkb_ctx;
 typedef struct zkb_bases zkb_bases;
@@ -50,6 +57,10 @@ int zkb_ctx_sync(zkb_ctx* ctx);
  * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
+/* page-locked (pinned, portable) host memory for witnesses / scalars: H2D copies from it run at PCIe
+ * speed and overlap with compute; plain malloc'ed buffers are accepted everywhere too (slower) */
+int zkb_host_alloc(uint64_t bytes, void** out);
+void zkb_host_free(void* p);
 
 /* ---- Fr NTT  (serves the 7 transforms of GenFinalProof) ---------------- */
 /* in place on a host buffer of 2^log_n canonical elements; ark-poly Radix2EvaluationDomain
@@ -158,6 +169,10 @@ void zkb_pk_free(zkb_pk* pk);
  * l_query is stored at the full witness length: its first 2 entries (the instance variables, which
  * ark-groth16 leaves out) are the point at infinity, so all witness MSMs share one scalar sort. */
 const zkb_bases* zkb_pk_query(const zkb_pk* pk, int which);
+/* number of variables m (the witness passed to the prove calls must hold exactly 32 * m bytes) and
+ * log2 of the QAP domain */
+uint64_t zkb_pk_n_vars(const zkb_pk* pk);
+uint32_t zkb_pk_log_n(const zkb_pk* pk);
 /* full witness assignment z (2^log_n canonical Fr, z[0] = 1, z[1] = public input) from two seeds */
 int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
                           uint8_t* z_out);

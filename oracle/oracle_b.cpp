@@ -632,15 +632,17 @@ int ob_threads() { return omp_get_max_threads(); }
 void ob_fr_ntt(uint8_t* data, unsigned log_n, int inverse, int coset) {
   size_t n = (size_t)1 << log_n;
   std::vector<U256> a(n);
-  for (size_t i = 0; i < n; i++) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; i++) {
     U256 c;
-    memcpy(c.w, data + 32 * i, 32);
+    memcpy(c.w, data + 32 * (size_t)i, 32);
     a[i] = to_m(c, FR);
   }
   fr_ntt_full(a, log_n, inverse != 0, coset != 0);
-  for (size_t i = 0; i < n; i++) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; i++) {
     U256 c = from_m(a[i], FR);
-    memcpy(data + 32 * i, c.w, 32);
+    memcpy(data + 32 * (size_t)i, c.w, 32);
   }
 }
 
@@ -719,6 +721,67 @@ void ob_random_scalars(uint64_t n, uint64_t seed, uint8_t* out) {
     U256 v = rng.fr();
     memcpy(out + 32 * i, v.w, 32);
   }
+}
+
+// ---- closed-form checkers for MSMs over the synthetic bases P_i = k_i * G:
+//      sum_i s_i P_i = (sum_i s_i k_i mod r) * G, so a 2^24..2^26-point MSM is checked with one
+//      O(n) dot product over Fr and ONE fixed-base multiplication.
+void ob_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+// out = sum_i a[i] * b[i] mod r   (canonical little-endian in and out)
+void ob_fr_dot(const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+  const int T = omp_get_max_threads();
+  std::vector<U256> part((size_t)T, U256{{0, 0, 0, 0}});
+#pragma omp parallel
+  {
+    U256 acc = {{0, 0, 0, 0}};
+#pragma omp for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+      U256 x, y;
+      memcpy(x.w, a + 32 * (size_t)i, 32);
+      memcpy(y.w, b + 32 * (size_t)i, 32);
+      // mmul(x, y) = x*y/R; one more Montgomery product with R^2 after the sum restores x*y
+      acc = madd(acc, mmul(x, y, FR), FR);
+    }
+    part[(size_t)omp_get_thread_num()] = acc;
+  }
+  U256 tot = {{0, 0, 0, 0}};
+  for (int t = 0; t < T; t++) tot = madd(tot, part[(size_t)t], FR);
+  tot = mmul(tot, FR.r2, FR);      // (sum x*y / R) * R^2 / R = sum x*y
+  memcpy(out, tot.w, 32);
+}
+// out = sum_i a[i] mod r
+void ob_fr_sum(const uint8_t* a, uint64_t n, uint8_t* out) {
+  U256 tot = {{0, 0, 0, 0}};
+  for (size_t i = 0; i < n; i++) {
+    U256 x;
+    memcpy(x.w, a + 32 * i, 32);
+    tot = madd(tot, x, FR);
+  }
+  memcpy(out, tot.w, 32);
+}
+// out = k * G1 generator / k * G2 generator (canonical affine)
+void ob_g1_mul_gen(const uint8_t* k, uint8_t* out) {
+  U256 s;
+  memcpy(s.w, k, 32);
+  Jac<Fq> acc = Jac<Fq>::identity(), base = {G1GEN.x, G1GEN.y, Fq::one()};
+  for (int i = 255; i >= 0; i--) {
+    acc = acc.dbl();
+    if ((s.w[i >> 6] >> (i & 63)) & 1) acc.add(base);
+  }
+  aff_put(acc.affine(), out);
+}
+void ob_g2_mul_gen(const uint8_t* k, uint8_t* out) {
+  U256 s;
+  memcpy(s.w, k, 32);
+  Aff<Fq2> g = g2gen();
+  Jac<Fq2> acc = Jac<Fq2>::identity(), base = {g.x, g.y, Fq2::one()};
+  for (int i = 255; i >= 0; i--) {
+    acc = acc.dbl();
+    if ((s.w[i >> 6] >> (i & 63)) & 1) acc.add(base);
+  }
+  aff_put(acc.affine(), out);
 }
 
 void* ob_setup_synthetic(unsigned log_n, uint64_t seed) { return setup_synthetic(log_n, seed); }

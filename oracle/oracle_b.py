@@ -38,6 +38,16 @@ def lib():
             f = getattr(l, "ob_synthetic_bases_" + g)
             f.argtypes = [u64, u64, vp]
             f.restype = None
+        l.ob_set_threads.argtypes = [C.c_int]
+        l.ob_set_threads.restype = None
+        l.ob_fr_dot.argtypes = [vp, vp, u64, vp]
+        l.ob_fr_dot.restype = None
+        l.ob_fr_sum.argtypes = [vp, u64, vp]
+        l.ob_fr_sum.restype = None
+        l.ob_g1_mul_gen.argtypes = [C.c_char_p, vp]
+        l.ob_g1_mul_gen.restype = None
+        l.ob_g2_mul_gen.argtypes = [C.c_char_p, vp]
+        l.ob_g2_mul_gen.restype = None
         l.ob_random_scalars.argtypes = [u64, u64, vp]
         l.ob_random_scalars.restype = None
         l.ob_setup_synthetic.argtypes = [C.c_uint, u64]
@@ -60,6 +70,57 @@ def lib():
 
 def threads() -> int:
     return lib().ob_threads()
+
+
+def set_threads(n: int = 0) -> int:
+    """use n OpenMP threads (0 = every core of the host), whatever OMP_NUM_THREADS says: torchrun
+    exports OMP_NUM_THREADS=1 to its workers, which would silently make the CPU baseline scalar."""
+    lib().ob_set_threads(n if n > 0 else (os.cpu_count() or 1))
+    return threads()
+
+
+def _ptr(data):
+    """bytes / bytearray / ctypes buffer / raw address -> something ctypes passes as void* without copying"""
+    if isinstance(data, int):
+        return C.c_void_p(data)
+    if isinstance(data, bytes):
+        return C.cast(C.c_char_p(data), C.c_void_p)
+    if isinstance(data, bytearray):
+        return C.cast((C.c_char * len(data)).from_buffer(data), C.c_void_p)
+    return C.cast(data, C.c_void_p)
+
+
+def fr_dot(a, b, n: int) -> bytes:
+    """sum a_i * b_i mod r over two arrays of n canonical scalars (bytes or raw host addresses)."""
+    out = C.create_string_buffer(32)
+    lib().ob_fr_dot(_ptr(a), _ptr(b), n, out)
+    return out.raw
+
+
+def fr_sum(a, n: int) -> bytes:
+    out = C.create_string_buffer(32)
+    lib().ob_fr_sum(_ptr(a), n, out)
+    return out.raw
+
+
+def g1_mul_gen(k: bytes) -> bytes:
+    out = C.create_string_buffer(64)
+    lib().ob_g1_mul_gen(bytes(k), out)
+    return out.raw
+
+
+def g2_mul_gen(k: bytes) -> bytes:
+    out = C.create_string_buffer(128)
+    lib().ob_g2_mul_gen(bytes(k), out)
+    return out.raw
+
+
+def msm_closed_form(scalars, n: int, bases_seed: int, g2=False) -> bytes:
+    """sum_i s_i * (k_i * G) for the synthetic bases of `bases_seed` (k_i = xoshiro256**(seed)),
+    computed as (sum s_i k_i mod r) * G: the size-independent check of a large MSM."""
+    ks = random_scalars(n, bases_seed)
+    d = fr_dot(scalars, ks, n)
+    return g2_mul_gen(d) if g2 else g1_mul_gen(d)
 
 
 def _buf(data: bytes):

@@ -19,6 +19,7 @@ pub const ZKB_ENOMEM: c_int = -3;
 pub const ZKB_EBUSY: c_int = -4;
 pub const ZKB_ENOGPU: c_int = -5;
 pub const ZKB_EVERIFY: c_int = -6;
+pub const ZKB_ECOMM: c_int = -7;
 pub const ZKB_VK_BYTES: usize = 576;
 pub const ZKB_PROOF_BYTES: usize = 256;
 pub const ZKB_INTERMEDIATE_BYTES: usize = 384;
@@ -74,6 +75,8 @@ extern "C" {
     pub fn zkb_ctx_sync(ctx: *mut zkb_ctx) -> c_int;
     pub fn zkb_ctx_set(ctx: *mut zkb_ctx, key: *const c_char, value: i64) -> c_int;
     pub fn zkb_version() -> *const c_char;
+    pub fn zkb_host_alloc(bytes: u64, out_: *mut *mut c_void) -> c_int;
+    pub fn zkb_host_free(p: *mut c_void);
     pub fn zkb_fr_ntt(ctx: *mut zkb_ctx, data: *mut u8, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
     pub fn zkb_fr_ntt_dev(ctx: *mut zkb_ctx, d_in: *const c_void, d_out: *mut c_void, log_n: u32, inverse: c_int, coset: c_int, montgomery: c_int) -> c_int;
     pub fn zkb_fr_ntt_batch_dev(ctx: *mut zkb_ctx, d_in: *const c_void, d_out: *mut c_void, log_size: u32, batch: u64, inverse: c_int, skip_ninv: c_int, d_pre_table: *const c_void, d_post_table: *const c_void) -> c_int;
@@ -106,6 +109,8 @@ extern "C" {
     pub fn zkb_pk_synthetic_shard_ex(ctx: *mut zkb_ctx, log_n: u32, seed: u64, rank: u32, world: u32, h_low_bits: u32, out_: *mut *mut zkb_pk, vk_out: *mut u8) -> c_int;
     pub fn zkb_pk_free(pk: *mut zkb_pk);
     pub fn zkb_pk_query(pk: *const zkb_pk, which: c_int) -> *const zkb_bases;
+    pub fn zkb_pk_n_vars(pk: *const zkb_pk) -> u64;
+    pub fn zkb_pk_log_n(pk: *const zkb_pk) -> u32;
     pub fn zkb_synthetic_witness(log_n: u32, w0: *const u8, w1: *const u8, z_out: *mut u8) -> c_int;
     pub fn zkb_groth16_prove(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8, intermediates_opt: *mut u8, h_out_opt: *mut u8, timings_opt: *mut zkb_prove_timings) -> c_int;
     pub fn zkb_groth16_prove_partial(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, partial_out: *mut u8, timings_opt: *mut zkb_prove_timings) -> c_int;

@@ -257,3 +257,38 @@ def test_cpp_example_proves_and_prints_reference_layout(tmp_path):
     assert pf.parse_public_input(input_txt)[0] < o.R
     # byte-identical to the library's own writer
     assert pf.proof_to_json(pf.proof_from_json(proof_txt)) == proof_txt.rstrip("\n")
+
+
+def test_get_batch_proof_view_matches_reference_rpc():
+    """eigenrpc_getBatchProof (reference src/custom_reth/eigen.rs:76-97): BATCH_PROOF_{n} -> BatchProofInfo
+    with the proof strings verbatim and 0x-hex state roots; a missing key is None."""
+    from eigen_zeth_b200 import proof_format as pf
+    pre, post = bytes(range(32)), bytes(range(255, 223, -1))
+    pr = pf.ProofResult(42, GOLDEN["proof_json"], GOLDEN["public_input_json"], pre, post)
+    db = {b"BATCH_PROOF_42": pr.to_json().encode(), b"BATCH_PROOF_43": b"{not a proof result"}
+    assert pf.batch_proof_key(42) == b"BATCH_PROOF_42"
+    info = pf.get_batch_proof(db.get, 42)
+    assert info.block_number == 42 and info.proof == GOLDEN["proof_json"] and info.public_input == GOLDEN["public_input_json"]
+    assert info.pre_state_root == "0x000102030405060708090a0b0c0d0e0f101112131415161718191a1b1c1d1e1f"
+    assert info.post_state_root == "0x" + post.hex() and len(info.post_state_root) == 66
+    assert json.loads(info.to_json())["pre_state_root"] == info.pre_state_root
+    assert list(json.loads(info.to_json())) == ["block_number", "proof", "public_input", "pre_state_root", "post_state_root"]
+    assert pf.get_batch_proof(db.get, 7) is None
+    with pytest.raises(ValueError):
+        pf.get_batch_proof(db.get, 43)
+    # the canned debug proof of the reference (worker.rs:49-96: post_state_root[24..] = batch le bytes) views cleanly
+    post_dbg = bytes(24) + (9).to_bytes(8, "little")
+    db[b"BATCH_PROOF_9"] = pf.ProofResult(9, "p", "i", bytes(32), post_dbg).to_json().encode()
+    assert pf.get_batch_proof(db.get, 9).post_state_root == "0x" + "00" * 24 + "0900000000000000"
+
+
+def test_python_binding_checks_buffer_lengths(zkb):
+    """the C ABI takes bare pointers; the binding refuses short buffers before they reach cudaMemcpy"""
+    class FakeCtx:
+        lib = zkb.load_library()
+    pk = zkb.lib.ProvingKey.__new__(zkb.lib.ProvingKey)
+    pk.n_vars = 16
+    with pytest.raises(ValueError, match="witness holds"):
+        pk.witness_ptr(bytes(32 * 15))
+    ptr, keep = pk.witness_ptr(bytes(32 * 16))
+    assert ptr.value and keep is not None

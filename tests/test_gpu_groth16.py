@@ -69,6 +69,26 @@ def test_prove_small_vs_oracle_a(ctx, zkb):
 
 
 @pytest.mark.parametrize("log_n", [18, 20])
+def test_prove_large_bit_exact_vs_oracle_b(ctx, zkb, log_n):
+    """h, the five MSM sums and the proof bytes at 2^18 / 2^20 constraints against oracle B (a pairing
+    check alone accepts any valid proof; this pins the intermediates too)."""
+    seed = 0x5EED0004 + log_n
+    pk = ctx.pk_synthetic(log_n, seed)
+    opk = ob.ProvingKey(log_n, seed)
+    assert pk.vk == opk.vk()
+    w0, w1, r, s = _inputs(seed + 1)
+    wit = zkb.synthetic_witness(log_n, w0, w1)
+    proof, inter, h, _ = ctx.groth16_prove(pk, wit, r, s, want_intermediates=True, want_h=True)
+    oproof, ointer, oh, _ = opk.prove(wit, r, s)
+    assert h == oh
+    assert inter == ointer
+    assert proof == oproof
+    assert zkb.groth16_verify(pk.vk, proof, wit[32:64])
+    pk.free()
+    opk.free()
+
+
+@pytest.mark.parametrize("log_n", [18, 20])
 def test_prove_large_pairing_verified(ctx, zkb, log_n):
     seed = 0x5EED0004 + log_n
     pk = ctx.pk_synthetic(log_n, seed)

@@ -177,3 +177,95 @@ def test_precomputed_g2_and_large_closed_form(ctx):
             assert o.g1_from_bytes(ctx.msm(big, fr_bytes([o.R - 1] * n))) == o.g1_mul(o.G1_GEN, (o.R - ksum) % o.R)
         finally:
             ctx.set("msm_host_chunks", 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# The benchmarked configuration (bench.py: 2^24 points, precomputed window multiples, c = 22) has
+# 2^21 buckets in ONE shared set, which takes the two-level bucket reduction (red_levels = 2,
+# msm_common.cu) with the `mul_small` fold of the last level (msm_impl.cuh).  Windows >= 21 reach
+# that path; small n keeps the oracle-A comparison cheap.
+@pytest.mark.parametrize("window", [21, 22, 23, 24])
+def test_wide_windows_two_level_bucket_reduction_g1(ctx, window):
+    n = 300
+    rng = o.Xoshiro256ss(7000 + window)
+    pts = _g1_points(rng, n)
+    pts[3] = None
+    pts[5] = pts[6]
+    pts[7] = o.g1_neg(pts[8])
+    bases = ctx.upload_bases(g1_bytes(pts))
+    assert bases.precompute(window) == window
+    top = (1 << (window - 1))            # the largest digit magnitude: last bucket of the set
+    cases = [rand_fr(rng, n), [o.R - 1] * n, [1] * n, [top] * n, [top - 1] * n, [(top << window) | top] * n,
+             [(i * 5) & 1 for i in range(n)], [0] * n]
+    for sc in cases:
+        sc = [s % o.R for s in sc]
+        assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g1(pts, sc), window
+    for chunks in (2, 3):                # the chunked host-scalar path merges bucket sets
+        ctx.set("msm_host_chunks", chunks)
+        try:
+            assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(cases[0]))) == o.msm_g1(pts, cases[0])
+        finally:
+            ctx.set("msm_host_chunks", 0)
+    bases.free()
+
+
+@pytest.mark.parametrize("window", [21, 23])
+def test_wide_windows_two_level_bucket_reduction_g2(ctx, window):
+    n = 90
+    rng = o.Xoshiro256ss(7100 + window)
+    pts = _g2_points(rng, n)
+    pts[1] = None
+    pts[4] = pts[5]
+    bases = ctx.upload_bases(g2_bytes(pts), g2=True)
+    assert bases.precompute(window) == window
+    top = 1 << (window - 1)
+    for sc in (rand_fr(rng, n), [o.R - 1] * n, [top] * n, [(i * 3) & 1 for i in range(n)]):
+        assert o.g2_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g2(pts, sc), window
+    bases.free()
+
+
+@pytest.mark.parametrize("log_n,window", [(22, 22), (24, 0)])
+def test_headline_msm_closed_form(ctx, log_n, window):
+    """The exact path bench.py times — 2^24 synthetic bases, zkb_bases_precompute (auto window = 22),
+    uniform scalars, device-resident AND host-scalar entry points — checked against the closed form
+    (sum s_i k_i mod r) * G computed by oracle B (one dot product over Fr + one scalar multiplication)."""
+    import torch
+    import oracle_b as ob
+    n, seed = 1 << log_n, 0x5EED0001 + log_n
+    bases = ctx.synthetic_bases(n, seed)
+    c = bases.precompute(window)
+    assert c == 22
+    sc = ob.random_scalars(n, 0x5EED0000 + log_n)
+    want = ob.msm_closed_form(sc, n, seed)
+    host = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
+    dev = host.cuda()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ctx.msm_dev(bases, dev.data_ptr(), n, out.data_ptr())
+    ctx.sync()
+    assert bytes(out.cpu().numpy()) == want                     # bench.py `value` path
+    assert ctx.msm_raw(bases, host.data_ptr(), n) == want       # bench.py `e2e` path (3 overlapped chunks)
+    # witness-like skew on the same bases: 0/1 scalars and one giant bucket
+    ks = ob.random_scalars(n, seed)
+    bits = bytearray(32 * n)
+    bits[0::64] = b"\x01" * (n // 2)                            # every even-indexed scalar is 1
+    t_bits = torch.frombuffer(bits, dtype=torch.uint8)
+    assert ctx.msm_raw(bases, t_bits.data_ptr(), n) == ob.msm_closed_form(bytes(bits), n, seed)
+    same = (0x1234567 << 200 | 99).to_bytes(32, "little")
+    ksum = ob.fr_sum(ks, n)
+    want_same = ob.g1_mul_gen(ob.fr_dot(same, ksum, 1))
+    all_same = bytearray(same * n)
+    t_same = torch.frombuffer(all_same, dtype=torch.uint8)
+    assert ctx.msm_raw(bases, t_same.data_ptr(), n) == want_same
+    bases.free()
+
+
+def test_g2_msm_closed_form_2p20(ctx):
+    import oracle_b as ob
+    n, seed = 1 << 20, 0x5EED0777
+    bases = ctx.synthetic_bases(n, seed, g2=True)
+    sc = ob.random_scalars(n, 4242)
+    want = ob.msm_closed_form(sc, n, seed, g2=True)
+    assert ctx.msm(bases, sc) == want
+    bases.precompute(0)
+    assert ctx.msm(bases, sc) == want
+    bases.free()

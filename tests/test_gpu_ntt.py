@@ -77,3 +77,25 @@ def test_launch_counter_counts_every_pass(ctx):
     ctx.fr_ntt_dev(x.data_ptr(), x.data_ptr(), 16, montgomery=True)
     ctx.sync()
     assert ctx.launches - before == 2
+
+
+@pytest.mark.parametrize("log_n", [16, 20, 24, 25, 26])
+def test_ntt_vs_oracle_b_large(ctx, log_n):
+    """The metric size (2^24, three passes 8+8+8) and the four-pass plans (2^25 = 7+6+6+6, 2^26) against
+    oracle B's ark-poly restatement, byte for byte; the inverse coset transform closes the loop."""
+    import oracle_b as ob
+    n = 1 << log_n
+    buf = ob.random_scalars(n, 0x5EED0002 + log_n)
+    want = ob.fr_ntt(buf)
+    got = ctx.fr_ntt(buf)
+    assert got == want
+    del want
+    if log_n <= 24:
+        assert ctx.fr_ntt(buf, inverse=True, coset=True) == ob.fr_ntt(buf, inverse=True, coset=True)
+        ctx.set("ntt_full_twiddles", 0)
+        try:
+            assert ctx.fr_ntt(buf) == got
+        finally:
+            ctx.set("ntt_full_twiddles", 1)
+    else:
+        assert ctx.fr_ntt(got, inverse=True) == buf

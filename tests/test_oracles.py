@@ -155,3 +155,23 @@ def test_oracle_b_groth16(log_n):
     assert o.g2_from_bytes(inter[128:256]) == ia["msm_b2"]
     assert g1_list(inter[256:]) == [ia["msm_l"], ia["msm_h"]]
     assert o.groth16_verify(vka, pa, [z[1]])
+
+
+def test_oracle_b_closed_form_helpers():
+    """the checkers bench.py and the large GPU tests rely on: sum s_i (k_i G) = (sum s_i k_i) G"""
+    n = 700
+    sc = ob.random_scalars(n, 5)
+    bs = ob.synthetic_bases(n, 7)
+    want, _ = ob.msm_g1(bs, sc)
+    assert ob.msm_closed_form(sc, n, 7) == want
+    vals = [int.from_bytes(sc[i * 32:i * 32 + 32], "little") for i in range(n)]
+    ks = ob.random_scalars(n, 7)
+    kv = [int.from_bytes(ks[i * 32:i * 32 + 32], "little") for i in range(n)]
+    assert int.from_bytes(ob.fr_sum(sc, n), "little") == sum(vals) % o.R
+    assert int.from_bytes(ob.fr_dot(sc, ks, n), "little") == sum(a * b for a, b in zip(vals, kv)) % o.R
+    assert ob.g1_mul_gen((12345).to_bytes(32, "little")) == o.g1_to_bytes(o.g1_mul(o.G1_GEN, 12345))
+    assert ob.g2_mul_gen((o.R - 1).to_bytes(32, "little")) == o.g2_to_bytes(o.g2_mul(o.G2_GEN, o.R - 1))
+    b2 = ob.synthetic_bases(40, 9, g2=True)
+    w2, _ = ob.msm_g2(b2, sc[:40 * 32])
+    assert ob.msm_closed_form(sc[:40 * 32], 40, 9, g2=True) == w2
+    assert ob.set_threads(0) >= 1

@@ -179,3 +179,77 @@ def test_service_proves_on_gpu_and_verifies():
         op.close()
     finally:
         srv.stop(0)
+
+
+def test_blinding_is_keyed_and_bound_to_the_whole_request():
+    """r, s must not be computable from public request fields, and one (r, s) must never
+    cover two different witnesses."""
+    from eigen_zeth_b200 import prover_service as ps
+    s1, s2 = b"\x01" * 32, b"\x02" * 32
+    r = ps._blinding(s1, "r", "batch", "proof", "addr")
+    assert len(r) == 32 and int.from_bytes(r, "little") < o.R
+    assert r == ps._blinding(s1, "r", "batch", "proof", "addr")              # replay: same blinding
+    assert r != ps._blinding(s2, "r", "batch", "proof", "addr")              # keyed by the server secret
+    assert r != ps._blinding(s1, "s", "batch", "proof", "addr")
+    assert r != ps._blinding(s1, "r", "batch", "other proof", "addr")        # another witness -> another r
+    assert r != ps._blinding(s1, "r", "batch", "proof", "other addr")
+    assert r != ps._blinding(s1, "r", "batc", "hproof", "addr")              # length-prefixed: no concatenation games
+    import hashlib
+    assert r != (int.from_bytes(hashlib.sha256(b"r" + b"batch").digest(), "little") & ((1 << 253) - 1)).to_bytes(32, "little")
+
+
+def test_secret_file_round_trip(tmp_path):
+    from eigen_zeth_b200 import prover_service as ps
+    path = str(tmp_path / "blinding.key")
+    a = ps.load_or_create_secret(path)
+    assert len(a) == 32 and ps.load_or_create_secret(path) == a
+    assert (os.stat(path).st_mode & 0o777) == 0o600
+    assert ps.load_or_create_secret(None) != ps.load_or_create_secret(None)
+
+
+def test_service_refuses_synthetic_setup_without_the_flag(capsys):
+    from eigen_zeth_b200 import prover_service as ps
+    with pytest.raises(SystemExit):
+        ps.main(["--log-n", "8"])
+    assert "insecure-synthetic-setup" in capsys.readouterr().err
+
+
+def test_handler_failure_answers_with_the_request_variant(server):
+    """the client forwards only same-variant responses (provider.rs:646-668); a handler bug
+    on a gen_batch_proof step must therefore be answered as gen_batch_proof, never as get_status."""
+    from eigen_zeth_b200 import protocol as pb
+    _, _, servicer = server
+
+    def boom(req):
+        raise RuntimeError("ledger exploded")
+
+    servicer._gen_batch_chunks = boom
+    servicer._gen_chunk_proof = boom
+    r = servicer.handle(pb.ProverRequest(id="1", gen_batch_proof=pb.GenBatchProofRequest(
+        gen_batch_chunks=pb.GenBatchChunks(batch_id="b1", batch=pb.Batch(block_number=[1]), chain_id=1, program_name="evm"))))
+    assert r.WhichOneof("response_type") == "gen_batch_proof"
+    res = r.gen_batch_proof.gen_batch_chunks
+    assert r.gen_batch_proof.WhichOneof("step") == "gen_batch_chunks" and res.result_code == pb.COMPLETED_ERROR
+    assert res.batch_id == "b1" and "ledger exploded" in res.error_message
+    assert len(res.pre_state_root) == 32 and len(res.post_state_root) == 32
+    r = servicer.handle(pb.ProverRequest(id="2", gen_batch_proof=pb.GenBatchProofRequest(
+        gen_chunk_proof=pb.GenChunkProof(batch_id="b1", task_id="t", chunk_count=1, batch_data="{}"))))
+    assert r.WhichOneof("response_type") == "gen_batch_proof"
+    assert r.gen_batch_proof.WhichOneof("step") == "gen_chunk_proof"
+    assert r.gen_batch_proof.gen_chunk_proof.result_code == pb.COMPLETED_ERROR
+
+
+def test_aggregate_step_prefetches_the_final_witness(server):
+    """the witness of GenFinalProof depends on the string handed out by GenAggregatedProof: the
+    servicer starts building it as soon as it hands that string out (it arrives back >= 1 s later,
+    provider.rs:542)."""
+    from operator_replay import OperatorReplay
+    addr, backend, servicer = server
+    seen = []
+    backend.prefetch = lambda rp, agg: seen.append((rp, agg))
+    op = OperatorReplay(addr, step_sleep=0.0)
+    op.execute(5, batch_id="pf-1")
+    op.close()
+    assert len(seen) == 1
+    rp, agg = seen[0]
+    assert agg == op.aggregator and len(rp) == 64
