@@ -183,8 +183,10 @@ int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out) {
 
 int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
             const void* pre_scale, const void* post_scale, int skip_ninv, int mont_in,
-            int mont_out, uint64_t batch) {
+            int mont_out, uint64_t batch, const NttRemap* remap) {
   if (batch == 0) return ZKB_OK;
+  if (remap && remap->in_ilv && (batch & (batch - 1)))
+    return set_error(ctx, ZKB_EINVAL, "element-major input needs a power-of-two batch");
   if (log_n < 1 || log_n > 28) return set_error(ctx, ZKB_EINVAL, "log_n must be in [1, 28]");
   int rc = ensure_stage_tables(ctx);
   if (rc) return rc;
@@ -207,6 +209,11 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, ctx->stream));
   }
   NttPassArgs a{};
+  a.xform_log = log_n;
+  if (remap && remap->in_ilv) {
+    a.in_ilv_log = 0;
+    while ((1ull << a.in_ilv_log) < batch) a.in_ilv_log++;
+  }
   a.flag = (uint32_t*)ctx->msm.flag.p;
   a.stage_tw = inverse ? ctx->stage_inv.p : ctx->stage_fwd.p;
   a.tw_lo = d->tw_lo.p;
@@ -222,6 +229,7 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
   for (size_t p = 0; p + 1 < P; p++) {
     uint32_t k = d->ks[p];
     a.in = p == 0 ? d_in : work;
+    a.in_ilv = (p == 0 && remap) ? remap->in_ilv : 0;
     a.out = work;
     a.k = k;
     a.M = M;
@@ -242,6 +250,12 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
   {
     uint32_t k = d->ks[P - 1];
     a.in = P == 1 ? d_in : work;
+    a.in_ilv = (P == 1 && remap) ? remap->in_ilv : 0;
+    if (remap && remap->out_win) {
+      a.out_win = 1;
+      a.out_col_bits = remap->out_col_bits;
+      for (int i = 0; i < 16; i++) a.out_wins[i] = remap->out_wins[i];
+    }
     a.out = d_out;
     a.k = k;
     a.tw_full = nullptr;
@@ -729,6 +743,12 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  for (auto& kv : ctx->dist_tables) {
+    kv.second->release();
+    delete kv.second;
+  }
+  ctx->dist_small.release();
   for (auto& kv : ctx->domains) {
     NttDomain* d = kv.second;
     d->tw_lo.release(); d->tw_hi.release(); d->tw_hi_ninv.release();
@@ -804,6 +824,14 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
     ctx->pk_precompute = value ? 1 : 0;
     return ZKB_OK;
   }
+  if (!std::strcmp(key, "comm_force_staging")) {   // before the first distributed call
+    ctx->comm_force_staging = value ? 1 : 0;
+    return ZKB_OK;
+  }
+  if (!std::strcmp(key, "msm_g2_pair")) {     // process-wide comparison switch, see msm_g2.cu
+    msm_set_g2_pair(value ? 1 : 0);
+    return ZKB_OK;
+  }
   if (!std::strcmp(key, "msm_profile")) {
     ctx->msm_profile = value ? 1 : 0;
     return ZKB_OK;
@@ -842,13 +870,6 @@ int zkb_fr_ntt_batch_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t l
   ZKB_ENTER(ctx);
   if (!d_in || !d_out) return set_error(ctx, ZKB_EINVAL, "null buffer");
   return ntt_run(ctx, d_in, d_out, log_size, inverse, d_pre_table, d_post_table, skip_ninv, 1, 1, batch);
-}
-int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, uint32_t b, uint32_t c) {
-  ZKB_ENTER(ctx);
-  if (!d_in || !d_out || d_in == d_out) return set_error(ctx, ZKB_EINVAL, "permute needs distinct buffers");
-  fr_permute_launch(d_in, d_out, a, b, c, ctx->stream);
-  ZKB_CUDA(ctx, cudaGetLastError());
-  return ZKB_OK;
 }
 int zkb_fr_gather_layout_dev(zkb_ctx* ctx, const void* d_full, void* d_out, uint32_t log_n, uint32_t low_bits,
                              uint32_t world, uint32_t rank) {

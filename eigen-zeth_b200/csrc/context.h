@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/zkb.h"
+#include "comm.h"
 #include "host_ff.hpp"
 #include "msm.h"
 #include "ntt.h"
@@ -92,6 +93,11 @@ struct zkb_ctx {
   zkb::DevBuf ntt_tmp;                     // ping-pong buffer of the multi-pass NTT
   zkb::DevBuf io_a, io_b, io_c;            // staging for the host-buffer entry points
   zkb::MsmScratch msm;
+  // multi-GPU (comm.cu / dist.cu)
+  zkb::Comm* comm = nullptr;
+  int64_t comm_force_staging = 0;          // test switch: NCCL send/recv staging even when peer mapping works
+  std::map<std::string, zkb::DevBuf*> dist_tables;   // four-step twiddle / index-power tables
+  zkb::DevBuf dist_small;                  // all-gather scratch of the distributed MSM / prove
 };
 
 namespace zkb {
@@ -116,9 +122,15 @@ int cuda_fail(zkb_ctx* ctx, cudaError_t e, const char* what);
 // internal device-level entry points (used by the C ABI wrappers and by the Groth16 pipeline)
 // `batch` contiguous transforms of 2^log_n elements each (tables, if given, cover the whole batch).
 // skip_ninv: an inverse transform without the 1/n factor (the caller folds it elsewhere).
+struct NttRemap {           // fused exchange of the four-step NTT, see NttPassArgs
+  int in_ilv = 0;           // input batch is element-major (i * batch + b); batch must be a power of two
+  int out_win = 0;          // output goes to per-rank windows instead of d_out
+  uint32_t out_col_bits = 0;
+  void* out_wins[16] = {};
+};
 int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
             const void* pre_scale, const void* post_scale, int skip_ninv, int mont_in,
-            int mont_out, uint64_t batch = 1);
+            int mont_out, uint64_t batch = 1, const NttRemap* remap = nullptr);
 int coset_tables(zkb_ctx* ctx, uint32_t log_n, CosetTables** out);
 int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars, uint64_t n,
              void* d_out_affine);
@@ -134,5 +146,16 @@ int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint
                           uint8_t* out);
 
 void host_fr_root(uint32_t log_n, int inverse, uint32_t out_mont[8]);
+
+// ---- distributed building blocks (dist.cu); collective over ctx->comm
+// one four-step transform of this rank's layout-`d` block x (n / world elements, Montgomery) into
+// layout log_n - d, in place; pre / post: optional element-wise tables in the input / output layout
+int dist_ntt_transform(zkb_ctx* ctx, void* d_x, uint32_t log_n, uint32_t d, int inverse, const void* d_pre,
+                       const void* d_post);
+// table[pos] = scale * base^{global index of pos} for this rank's layout-d block (Montgomery words in)
+int dist_index_power_table(zkb_ctx* ctx, uint32_t log_n, uint32_t d, const host::HFr& base,
+                           const host::HFr& scale, const void** out);
+// out = sum over the ranks of this rank's affine point (64 / 128 canonical bytes, device)
+int dist_point_allreduce(zkb_ctx* ctx, const void* d_point, int is_g2, void* d_out);
 
 }  // namespace zkb

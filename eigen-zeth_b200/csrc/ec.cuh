@@ -19,16 +19,16 @@ struct Affine {
   __device__ __forceinline__ bool is_inf() const { return x.raw_is_zero() && y.raw_is_zero(); }
   __device__ __forceinline__ static Affine load_nc(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
-    return {F::load_nc(c), F::load_nc(c + sizeof(F))};
+    return {F::load_nc(c), F::load_nc(c + F::kBytes)};
   }
   __device__ __forceinline__ static Affine load(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
-    return {F::load(c), F::load(c + sizeof(F))};
+    return {F::load(c), F::load(c + F::kBytes)};
   }
   __device__ __forceinline__ void store(void* p) const {
     char* c = reinterpret_cast<char*>(p);
     x.store(c);
-    y.store(c + sizeof(F));
+    y.store(c + F::kBytes);
   }
 };
 
@@ -46,15 +46,15 @@ struct XYZZ {
   }
   __device__ __forceinline__ static XYZZ load(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
-    return {F::load(c), F::load(c + sizeof(F)), F::load(c + 2 * sizeof(F)),
-            F::load(c + 3 * sizeof(F))};
+    return {F::load(c), F::load(c + F::kBytes), F::load(c + 2 * F::kBytes),
+            F::load(c + 3 * F::kBytes)};
   }
   __device__ __forceinline__ void store(void* p) const {
     char* c = reinterpret_cast<char*>(p);
     x.store(c);
-    y.store(c + sizeof(F));
-    zz.store(c + 2 * sizeof(F));
-    zzz.store(c + 3 * sizeof(F));
+    y.store(c + F::kBytes);
+    zz.store(c + 2 * F::kBytes);
+    zzz.store(c + 3 * F::kBytes);
   }
   __device__ __forceinline__ XYZZ neg() const { return {x, y.neg(), zz, zzz}; }
 
@@ -177,6 +177,9 @@ using G1Affine = Affine<Fq>;
 using G2Affine = Affine<Fq2>;
 using G1XYZZ = XYZZ<Fq>;
 using G2XYZZ = XYZZ<Fq2>;
+// storage sizes (identical for Fq2 and its lane-pair form Fq2L)
+template <class F> constexpr size_t affine_bytes() { return 2 * size_t(F::kBytes); }
+template <class F> constexpr size_t xyzz_bytes() { return 4 * size_t(F::kBytes); }
 
 #endif
 }  // namespace zkb

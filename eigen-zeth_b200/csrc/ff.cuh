@@ -425,6 +425,8 @@ template <class P>
 struct Fp {
   uint32_t v[8];
   using Params = P;
+  static constexpr int kBytes = 32;   // storage size
+  static constexpr int kLanes = 1;    // threads that hold one element
 
   __device__ __forceinline__ static Fp zero() {
     Fp r;
@@ -601,6 +603,8 @@ using Fr = Fp<FrParams>;
 // ---------------------------------------------------------------- Fq2 = Fq[u]/(u^2+1)
 struct Fq2 {
   Fq c0, c1;
+  static constexpr int kBytes = 64;
+  static constexpr int kLanes = 1;
   __device__ __forceinline__ static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
   __device__ __forceinline__ static Fq2 one() { return {Fq::one(), Fq::zero()}; }
   __device__ __forceinline__ static Fq2 load(const void* p) {
@@ -650,6 +654,96 @@ struct Fq2 {
   __device__ Fq2 inverse() const {
     Fq d = (c0.sqr() + c1.sqr()).inverse();
     return {c0 * d, (c1 * d).neg()};
+  }
+};
+
+// ---------------------------------------------------------------- Fq2 split over a lane pair
+// One Fq2 element held by TWO adjacent lanes of a warp: the even lane owns c0, the odd lane c1.
+// The memory layout is that of Fq2 (c0 | c1, 64 bytes); only the register distribution differs.
+// Why: an XYZZ accumulator over Fq2 plus a prefetched point needs > 200 registers in one thread, which
+// caps the G2 bucket walk at 8 warps per SM and leaves the IMAD.WIDE pipe idle a third of the time
+// (2 warps per scheduler cannot cover a 136-deep carry chain).  Split over a pair, each lane carries
+// exactly what a G1 lane carries (one Fq per coordinate) and the walk runs at 16 warps per SM.
+//   (a0 + a1 u)(b0 + b1 u):  even lane  a0 b0 + (-a1) b1      odd lane  a1 b0 + a0 b1
+// both are ONE fused dual product (mont_mul2) on  own_a * P + recv * Q  with recv = the partner's
+// a-component (the odd lane sends -a1) and (P, Q) = (b, b') / (b', b): 16 shuffles and a few selects
+// per Fq2 product, against 200 IMAD.WIDE.  Squaring: even (a0 + a1)(a0 - a1), odd (a1 + a1) a0.
+// All shuffles name only the two lanes of the pair, which always take the same branches, so pairs of
+// one warp may diverge from each other freely.  Block sizes must be even (they are multiples of 32).
+__device__ __forceinline__ uint32_t pair_half() { return threadIdx.x & 1u; }
+__device__ __forceinline__ uint32_t pair_mask() { return 3u << (threadIdx.x & 30u); }
+__device__ __forceinline__ Fq pair_swap(const Fq& a) {
+  Fq r;
+  const uint32_t m = pair_mask();
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(m, a.v[i], 1);
+  return r;
+}
+__device__ __forceinline__ bool pair_all(bool x) {
+  // the shuffle must be executed by BOTH lanes whatever x is (no short-circuit in front of it)
+  const int other = __shfl_xor_sync(pair_mask(), int(x), 1);
+  return x & (other != 0);
+}
+__device__ __forceinline__ Fq fq_select(bool c, const Fq& a, const Fq& b) {   // c ? a : b, branch-free
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
+// 2p - a  (a in [0, 2p]  ->  result in [0, 2p]: a valid multiplier operand of mont_mul / mont_mul2)
+__device__ __forceinline__ Fq fq_neg_2p(const Fq& a) {
+  Fq r;
+  sub256(r.v, Fq::modulus2().v, a.v);
+  return r;
+}
+
+struct Fq2L {
+  Fq v;                               // c0 on even lanes, c1 on odd lanes
+  static constexpr int kBytes = 64;
+  static constexpr int kLanes = 2;
+  __device__ __forceinline__ static Fq2L zero() { return {Fq::zero()}; }
+  __device__ __forceinline__ static Fq2L one() { return {fq_select(pair_half() != 0, Fq::zero(), Fq::one())}; }
+  __device__ __forceinline__ static Fq2L load(const void* p) {
+    return {Fq::load(reinterpret_cast<const char*>(p) + 32 * pair_half())};
+  }
+  __device__ __forceinline__ static Fq2L load_nc(const void* p) {
+    return {Fq::load_nc(reinterpret_cast<const char*>(p) + 32 * pair_half())};
+  }
+  __device__ __forceinline__ void store(void* p) const { v.store(reinterpret_cast<char*>(p) + 32 * pair_half()); }
+  __device__ __forceinline__ friend Fq2L operator+(const Fq2L& a, const Fq2L& b) { return {a.v + b.v}; }
+  __device__ __forceinline__ friend Fq2L operator-(const Fq2L& a, const Fq2L& b) { return {a.v - b.v}; }
+  __device__ __forceinline__ friend Fq2L operator*(const Fq2L& a, const Fq2L& b) {
+    const bool odd = pair_half() != 0;
+    const Fq send = fq_select(odd, fq_neg_2p(a.v), a.v);     // the odd lane hands over -a1
+    const Fq recv = pair_swap(send);                          // even: -a1      odd: a0
+    const Fq bp = pair_swap(b.v);                             // the partner's b component
+    const Fq P = fq_select(odd, bp, b.v);                     // even: b0       odd: b0
+    const Fq Q = fq_select(odd, b.v, bp);                     // even: b1       odd: b1
+    return {Fq::mul_add_mul(a.v, P, recv, Q)};                // even: a0 b0 - a1 b1   odd: a1 b0 + a0 b1
+  }
+  __device__ __forceinline__ static Fq2L mul_sub_mul(const Fq2L& a, const Fq2L& b, const Fq2L& c, const Fq2L& d) {
+    return a * b - c * d;
+  }
+  __device__ __forceinline__ Fq2L sqr() const {
+    const bool odd = pair_half() != 0;
+    const Fq o = pair_swap(v);
+    const Fq U = v + fq_select(odd, v, o);                    // even: a0 + a1   odd: 2 a1
+    const Fq V = fq_select(odd, o, v - o);                    // even: a0 - a1   odd: a0
+    return {U * V};
+  }
+  __device__ __forceinline__ Fq2L dbl() const { return {v.dbl()}; }
+  __device__ __forceinline__ Fq2L neg() const { return {v.neg()}; }
+  __device__ __forceinline__ bool is_zero() const { return pair_all(v.is_zero()); }
+  __device__ __forceinline__ bool raw_is_zero() const { return pair_all(v.raw_is_zero()); }
+  __device__ __forceinline__ friend bool operator==(const Fq2L& a, const Fq2L& b) { return (a - b).is_zero(); }
+  __device__ __forceinline__ Fq2L to_mont() const { return {v.to_mont()}; }
+  __device__ __forceinline__ Fq2L from_mont() const { return {v.from_mont()}; }
+  __device__ __forceinline__ Fq2L reduced() const { return {v.reduced()}; }
+  __device__ Fq2L inverse() const {
+    const Fq sq = v.sqr();
+    const Fq d = (sq + pair_swap(sq)).inverse();              // 1 / (c0^2 + c1^2), computed by both lanes
+    const Fq r = v * d;
+    return {fq_select(pair_half() != 0, r.neg(), r)};
   }
 };
 

@@ -42,7 +42,7 @@ struct zkb_pk {
   // full query (q = 0 a, 1 b_g1, 2 b_g2, 3 l, 4 h); world == 1 means the whole key
   uint32_t n_inst = 2;       // instance variables incl. the constant one: z[0] = 1, z[1..n_inst)
   uint32_t rank = 0, world = 1;
-  uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (dist_ntt.py)
+  uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (csrc/dist.cu)
   uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
   // the prove entry points write the key's work vectors (d_a..d_zm, d_results, d_proof) behind a
   // const zkb_pk*: one prove at a time per key, whatever context it is called through
@@ -59,6 +59,8 @@ struct PkGuard {
 }  // namespace zkb
 
 namespace zkb {
+int dist_sum_blocks(zkb_ctx* ctx, const void* d_block, uint32_t bytes, const uint32_t* offs, const uint32_t* g2s,
+                    uint32_t n_slots, void* d_out);   // dist.cu
 
 // ---------------------------------------------------------------- kernels
 __global__ void fr_to_mont_copy_kernel(const Fr* in, Fr* out, uint64_t n) {
@@ -76,7 +78,7 @@ __global__ void r1cs_spmv_kernel(const uint32_t* __restrict__ row_ptr, const uin
   uint64_t pos = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (pos >= n) return;
   // low_bits == 0: out[j] for every row j < n.  Otherwise only this rank's block of "layout d"
-  // (dist_ntt.py): out[low_loc * H + high] = row (low0 + low_loc) + (high << low_bits), n = lows * H.
+  // (csrc/dist.cu): out[low_loc * H + high] = row (low0 + low_loc) + (high << low_bits), n = lows * H.
   uint64_t j = pos;
   if (low_bits) {
     const uint32_t hbits = log_n - low_bits;
@@ -784,14 +786,17 @@ static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[
 }
 
 // witness -> a, b, c evaluation vectors (Montgomery, natural order) in pk->d_a / d_b / d_c
+// (witness == nullptr: the caller has already staged the canonical witness in pk->d_z)
 static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness,
                                uint32_t low_bits = 0, uint32_t world = 1, uint32_t rank = 0,
                                void* const* d_out_opt = nullptr) {
   const uint64_t n = pk->n, m = pk->m;
   cudaStream_t st = ctx->stream;
-  ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
-  ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st));
+  if (witness) {
+    ZKB_CUDA(ctx, ctx->msm.flag.ensure(16));
+    ZKB_CUDA(ctx, cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st));
+  }
   const uint32_t bl_m = uint32_t((m + 255) / 256);
   fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
   count_launches(4);   // + the three SpMV launches below
@@ -813,15 +818,23 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
   return ZKB_OK;
 }
 
-// witness MSMs over pk's ranges + H MSM with h taken from d_h (canonical, pk's local h order)
-static int prove_msm_only_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, uint8_t* results_out) {
+// the five MSMs over pk's ranges into pk->d_results (device, asynchronous); h from d_h (canonical,
+// pk's local h order)
+static int prove_msm_dev_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, cudaEvent_t ev_witness_msms = nullptr) {
   char* res = (char*)pk->d_results;
   const char* z = (const char*)pk->d_z;
   const zkb_bases* qs[4] = {pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query};
   void* outs4[4] = {res, res + 64, res + 256, res + 128};
   int rc = msm_exec_multi(ctx, qs, 4, z + 32 * pk->qfirst[0], 0, pk->qcount[0], outs4, nullptr);
   if (rc) return rc;
-  if ((rc = msm_exec(ctx, pk->h_query, 0, d_h, pk->qcount[4], res + 320))) return rc;
+  if (ev_witness_msms) cudaEventRecord(ev_witness_msms, ctx->stream);
+  return msm_exec(ctx, pk->h_query, 0, d_h, pk->qcount[4], res + 320);
+}
+
+// witness MSMs over pk's ranges + H MSM with h taken from d_h (canonical, pk's local h order)
+static int prove_msm_only_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, uint8_t* results_out) {
+  int rc = prove_msm_dev_phase(ctx, pk, d_h);
+  if (rc) return rc;
   uint32_t bad_flag = 0;
   ZKB_CUDA(ctx, cudaMemcpyAsync(results_out, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   ZKB_CUDA(ctx, cudaMemcpyAsync(&bad_flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -900,6 +913,106 @@ int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
   ZKB_PK_ENTER(ctx, pk);
   if (!d_h || !partial_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   return prove_msm_only_phase(ctx, pk, d_h, partial_out);
+}
+
+// ---- the whole proof over the ranks of ctx's communicator (collective; BASELINE.json configs[4])
+int zkb_pk_synthetic_dist(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]) {
+  if (!ctx) return ZKB_EINVAL;
+  if (!ctx->comm) return set_error(ctx, ZKB_EINVAL, "no communicator (zkb_comm_init first)");
+  const uint32_t world = uint32_t(ctx->comm->world), d0 = log_n / 2;
+  if (log_n < 4 || ((1u << d0) % world))
+    return set_error(ctx, ZKB_EINVAL, "circuit too small for this many ranks (need 2^(log_n/2) >= world)");
+  return zkb_pk_synthetic_shard_ex(ctx, log_n, seed, uint32_t(ctx->comm->rank), world, log_n - d0, out, vk_out);
+}
+
+int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
+                           const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES], zkb_prove_timings* timings_opt) {
+  ZKB_PK_ENTER(ctx, pk);
+  if (!witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  Comm* cm = ctx->comm;
+  if (!cm) return set_error(ctx, ZKB_EINVAL, "no communicator (zkb_comm_init first)");
+  const uint32_t L = pk->log_n, d0 = L / 2, d1 = L - d0, G = uint32_t(cm->world), g = uint32_t(cm->rank);
+  if (pk->world != G || pk->rank != g || pk->h_low_bits != d1)
+    return set_error(ctx, ZKB_EINVAL, "key was not built for this communicator (use zkb_pk_synthetic_dist)");
+  const uint64_t n = pk->n, m = pk->m, n_loc = n / G;
+  cudaStream_t st = ctx->stream;
+  enum { E_START, E_WIT, E_SPMV, E_NTT, E_MSMW, E_MSMH, E_END, E_COUNT };
+  cudaEvent_t ev[E_COUNT];
+  for (int i = 0; i < E_COUNT; i++) ZKB_CUDA(ctx, cudaEventCreate(&ev[i]));
+  int rc = ZKB_OK;
+  do {
+    cudaEventRecord(ev[E_START], st);
+    cudaError_t e0 = ctx->msm.flag.ensure(16);
+    if (e0 == cudaSuccess) e0 = ctx->dist_small.ensure(size_t(kMaxRanks) * 512 + 1024);
+    if (e0 != cudaSuccess) { rc = cuda_fail(ctx, e0, "scratch"); break; }
+    cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);
+    // 1. witness: every rank uploads 1/G of it over PCIe, the slices travel over NVLink
+    cudaPointerAttributes attr;
+    const bool on_device = cudaPointerGetAttributes(&attr, witness) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (on_device || G == 1) {
+      cudaMemcpyAsync(pk->d_z, witness, m * 32, cudaMemcpyDefault, st);
+    } else {
+      const uint64_t per = m * 32 / G;
+      char* mine = (char*)pk->d_z + g * per;
+      cudaMemcpyAsync(mine, witness + g * per, per, cudaMemcpyHostToDevice, st);
+      if ((rc = comm_allgather(ctx, mine, pk->d_z, per))) break;
+    }
+    cudaEventRecord(ev[E_WIT], st);
+    // 2. A z, B z, C z: only the rows of this rank's layout-d0 block
+    void* bufs[3] = {pk->d_a, pk->d_b, pk->d_c};
+    if ((rc = prove_witness_phase(ctx, pk, nullptr, d0, G, g, bufs))) break;
+    cudaEventRecord(ev[E_SPMV], st);
+    // 3. the witness map: 7 four-step transforms, coset shifts and 1/Z(g) folded into index tables
+    const HFr gen = HFr::from_u64(5);
+    const HFr zinv = (hpow_u64(gen, n) - HFr::one()).inverse();
+    const void *t_coset = nullptr, *t_uncoset = nullptr;
+    if ((rc = dist_index_power_table(ctx, L, d1, gen, HFr::one(), &t_coset))) break;
+    if ((rc = dist_index_power_table(ctx, L, d1, gen.inverse(), zinv, &t_uncoset))) break;
+    for (int k = 0; k < 3 && !rc; k++) rc = dist_ntt_transform(ctx, bufs[k], L, d0, 1, nullptr, t_coset);
+    for (int k = 0; k < 3 && !rc; k++) rc = dist_ntt_transform(ctx, bufs[k], L, d1, 0, nullptr, nullptr);
+    if (rc) break;
+    fr_mul_sub_launch(pk->d_a, pk->d_b, pk->d_c, n_loc, st);
+    if ((rc = dist_ntt_transform(ctx, pk->d_a, L, d0, 1, nullptr, t_uncoset))) break;
+    fr_convert_launch(pk->d_a, n_loc, 0, st);
+    cudaEventRecord(ev[E_NTT], st);
+    // 4. the five MSMs over this rank's point ranges
+    if ((rc = prove_msm_dev_phase(ctx, pk, pk->d_a, ev[E_MSMW]))) break;
+    cudaEventRecord(ev[E_MSMH], st);
+    // 5. 384 bytes per rank: all-gather, slot-wise sums, assemble — all on the device
+    static const uint32_t offs[5] = {0, 64, 128, 256, 320}, g2s[5] = {0, 0, 1, 0, 0};
+    if ((rc = dist_sum_blocks(ctx, pk->d_results, ZKB_INTERMEDIATE_BYTES, offs, g2s, 5, pk->d_results))) break;
+    // a non-canonical witness element is seen only by the rank whose MSM shard holds it: share the flags
+    char* fl = (char*)ctx->dist_small.p + 512;
+    cudaMemcpyAsync(fl, ctx->msm.flag.p, 4, cudaMemcpyDeviceToDevice, st);
+    if ((rc = comm_allgather(ctx, fl, fl + 64, 4))) break;
+    uint32_t flags[kMaxRanks] = {};
+    cudaMemcpyAsync(flags, fl + 64, 4 * G, cudaMemcpyDeviceToHost, st);
+    float ms_asm = 0;
+    if ((rc = prove_assemble_phase(ctx, pk, r, s, proof_out, &ms_asm))) break;   // synchronises
+    cudaEventRecord(ev[E_END], st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "distributed prove"); break; }
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < G; i++) bad |= flags[i];
+    if (bad & 1) {
+      cudaMemsetAsync(ctx->msm.flag.p, 0, 16, st);
+      std::memset(proof_out, 0, ZKB_PROOF_BYTES);
+      rc = set_error(ctx, ZKB_EINVAL, "non-canonical Fr element in the witness");
+      break;
+    }
+    if (timings_opt) {
+      std::memset(timings_opt, 0, sizeof(*timings_opt));
+      cudaEventElapsedTime(&timings_opt->ms_h2d, ev[E_START], ev[E_WIT]);
+      cudaEventElapsedTime(&timings_opt->ms_spmv, ev[E_WIT], ev[E_SPMV]);
+      cudaEventElapsedTime(&timings_opt->ms_ntt, ev[E_SPMV], ev[E_NTT]);
+      cudaEventElapsedTime(&timings_opt->ms_msm_a, ev[E_NTT], ev[E_MSMW]);     // A + B1 + L + B2 (one sort)
+      cudaEventElapsedTime(&timings_opt->ms_msm_h, ev[E_MSMW], ev[E_MSMH]);
+      cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_END]);
+    }
+  } while (0);
+  for (int i = 0; i < E_COUNT; i++) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],

@@ -21,6 +21,7 @@ struct MsmPlan {
   uint64_t n_buckets;       // n_sets * half (also the sentinel key of zero digits)
   uint64_t m;               // n * nwin (key, value) pairs
   int key_bits;             // radix-sort key width
+  int g2_pair;              // G2 only: level-1 walk splits one Fq2 point operation over a lane pair
   uint32_t l1_threads;      // chunks of the level-1 walk
   uint32_t l2_len;          // chunk length of the level-2 walk
   uint32_t l2_threads;
@@ -54,7 +55,10 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
 int msm_auto_window(uint64_t n, bool precomputed);
 // resident threads per SM the level-1 walk kernel of each curve is compiled for (launch bounds)
 uint32_t msm_l1_threads_per_sm_g1();
-uint32_t msm_l1_threads_per_sm_g2();
+uint32_t msm_l1_threads_per_sm_g2(int pair);
+// process-wide comparison switch (zkb_ctx_set "msm_g2_pair"): 1 = lane-pair G2 walk (default)
+void msm_set_g2_pair(int on);
+int msm_get_g2_pair();
 // out[w * n + i] = 2^{c w} * in[i], w < nwin (affine Montgomery in and out; in may alias out[0..n))
 void msm_precompute_g1(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);
 void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s);

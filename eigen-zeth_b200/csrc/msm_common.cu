@@ -13,6 +13,9 @@ namespace zkb {
 static std::atomic<uint64_t> g_launches{0};
 void count_launches(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+static std::atomic<int> g_g2_pair{1};
+void msm_set_g2_pair(int on) { g_g2_pair.store(on ? 1 : 0); }
+int msm_get_g2_pair() { return g_g2_pair.load(); }
 
 // ---------------------------------------------------------------- 1. digits
 __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t c,
@@ -112,7 +115,8 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
   p.key_bits = 1;
   while ((1ull << p.key_bits) <= p.n_buckets) p.key_bits++;   // sentinel == n_buckets must fit
   // level-1 threads: one resident wave, never less than 8 entries per thread
-  uint32_t per_sm = is_g2 ? msm_l1_threads_per_sm_g2() : msm_l1_threads_per_sm_g1();
+  p.g2_pair = is_g2 ? msm_get_g2_pair() : 0;
+  uint32_t per_sm = is_g2 ? msm_l1_threads_per_sm_g2(p.g2_pair) : msm_l1_threads_per_sm_g1();
   uint64_t t1 = uint64_t(sm_count) * per_sm;
   uint64_t cap = (p.m + 7) / 8;
   if (cap < 1) cap = 1;

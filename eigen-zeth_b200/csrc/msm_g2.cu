@@ -4,7 +4,10 @@
 namespace zkb {
 void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
                        cudaStream_t s) {
-  msm_accumulate_t<Fq2>(p, b, d_bases, bucket_target, s);
+  // level-1 walk with one Fq2 point operation split over a lane pair (Fq2L, 16 warps / SM) unless
+  // the comparison switch asks for the one-thread-per-point walk (8 warps / SM, 255 registers)
+  if (p.g2_pair) msm_accumulate_t<Fq2, Fq2L>(p, b, d_bases, bucket_target, s);
+  else msm_accumulate_t<Fq2, Fq2>(p, b, d_bases, bucket_target, s);
 }
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
   msm_merge_t<Fq2>(p, main_buckets, part_buckets, s);
@@ -19,5 +22,8 @@ void msm_sum_affine_g2(const void* d_pts, uint32_t n, void* d_out, cudaStream_t 
 void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin, uint32_t c, cudaStream_t s) {
   msm_precompute_t<Fq2>(d_in, d_out, n, nwin, c, s);
 }
-uint32_t msm_l1_threads_per_sm_g2() { return 128u * L1Cfg<Fq2>::kMinBlocks; }
+// chunks (not threads) walked concurrently per SM
+uint32_t msm_l1_threads_per_sm_g2(int pair) {
+  return pair ? 128u * L1Cfg<Fq2L>::kMinBlocks / Fq2L::kLanes : 128u * L1Cfg<Fq2>::kMinBlocks;
+}
 }  // namespace zkb

@@ -31,18 +31,23 @@ namespace zkb {
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 
 // resident CTAs (of 128 threads) per SM for the level-1 walk: 4 x 128 threads at <= 128 registers
-// for G1; the Fq2 accumulator needs the full 255 registers, so 2 x 128 for G2
+// for G1 and for G2 split over lane pairs (Fq2L, ff.cuh); the one-thread-per-point Fq2 walk needs the
+// full 255 registers, so 2 x 128 (kept for comparison: ctx tunable "msm_g2_pair" = 0)
 template <class F> struct L1Cfg { static constexpr int kMinBlocks = 4; };
 template <> struct L1Cfg<Fq2> { static constexpr int kMinBlocks = 2; };
 
 // ---------------------------------------------------------------- 3. accumulate, level 1
+// F is the register-level field type of the walk (Fq, Fq2, or Fq2L = one Fq2 over a lane pair);
+// memory is addressed in bytes so that Fq2 and Fq2L share one layout.  A chunk is walked by
+// F::kLanes adjacent lanes.
 template <class F>
 __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_kernel(
     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-    const uint64_t* __restrict__ m_valid_ptr, const Affine<F>* __restrict__ bases,
-    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
-    XYZZ<F>* __restrict__ part_pts, uint32_t n_threads) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t* __restrict__ m_valid_ptr, const char* __restrict__ bases,
+    char* __restrict__ buckets, uint32_t* __restrict__ part_keys,
+    char* __restrict__ part_pts, uint32_t n_threads) {
+  constexpr size_t kAff = 2 * size_t(F::kBytes), kPt = 4 * size_t(F::kBytes);
+  uint32_t tid = (blockIdx.x * blockDim.x + threadIdx.x) / F::kLanes;
   if (tid >= n_threads) return;
   const uint64_t m_valid = *m_valid_ptr;
   const uint64_t len = (m_valid + n_threads - 1) / n_threads;
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_k
     return;
   }
   uint32_t key_n = keys[start], val_n = vals[start];
-  Affine<F> pt_n = Affine<F>::load_nc(bases + (val_n & 0x7fffffffu));
+  Affine<F> pt_n = Affine<F>::load_nc(bases + size_t(val_n & 0x7fffffffu) * kAff);
   uint32_t cur = key_n;
   bool first_run = true;
   XYZZ<F> acc = XYZZ<F>::infinity();
@@ -64,15 +69,15 @@ __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_k
     if (i + 1 < end) {
       key_n = keys[i + 1];
       val_n = vals[i + 1];
-      pt_n = Affine<F>::load_nc(bases + (val_n & 0x7fffffffu));
+      pt_n = Affine<F>::load_nc(bases + size_t(val_n & 0x7fffffffu) * kAff);
     }
     if (key != cur) {
       if (first_run) {
         part_keys[2 * tid] = cur;
-        acc.store(part_pts + 2 * tid);
+        acc.store(part_pts + size_t(2 * tid) * kPt);
         first_run = false;
       } else {
-        acc.store(buckets + cur);
+        acc.store(buckets + size_t(cur) * kPt);
       }
       acc = XYZZ<F>::infinity();
       cur = key;
@@ -82,11 +87,11 @@ __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_k
   }
   if (first_run) {
     part_keys[2 * tid] = cur;
-    acc.store(part_pts + 2 * tid);
+    acc.store(part_pts + size_t(2 * tid) * kPt);
     part_keys[2 * tid + 1] = kInvalidKey;
   } else {
     part_keys[2 * tid + 1] = cur;
-    acc.store(part_pts + 2 * tid + 1);
+    acc.store(part_pts + size_t(2 * tid + 1) * kPt);
   }
 }
 
@@ -303,15 +308,17 @@ __global__ void __launch_bounds__(128) msm_bucket_merge_kernel(XYZZ<F>* __restri
   m.store(main_b + j);
 }
 
-// sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first)
-template <class F>
+// sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first).
+// FW is the register-level field type of the level-1 walk (F itself, or Fq2L for F = Fq2).
+template <class F, class FW = F>
 void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases,
                       void* bucket_target, cudaStream_t s) {
   using P = XYZZ<F>;
+  static_assert(F::kBytes == FW::kBytes, "walk type must share the storage layout");
   cudaMemsetAsync(bucket_target, 0, p.n_buckets * sizeof(P), s);
-  msm_accumulate_l1_kernel<F><<<(p.l1_threads + 127) / 128, 128, 0, s>>>(
-      b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const Affine<F>*>(d_bases),
-      reinterpret_cast<P*>(bucket_target), b.part1_keys, reinterpret_cast<P*>(b.part1_pts),
+  msm_accumulate_l1_kernel<FW><<<(p.l1_threads * FW::kLanes + 127) / 128, 128, 0, s>>>(
+      b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const char*>(d_bases),
+      reinterpret_cast<char*>(bucket_target), b.part1_keys, reinterpret_cast<char*>(b.part1_pts),
       p.l1_threads);
   count_launches(1);
   if (b.ev) cudaEventRecord(b.ev[3], s);

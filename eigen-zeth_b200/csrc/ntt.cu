@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
       uint64_t idx;
       if (!FINAL) idx = base + uint64_t(t) * p.S + c;
       else idx = batch_off + ((uint64_t(c_base + c) << mid_bits) + mid) * (1u << k) + t;
-      x = Fr::load_nc(in + idx * 32);
+      uint64_t src = idx;
+      if (p.in_ilv) src = ((idx & ((1ull << p.xform_log) - 1)) << p.in_ilv_log) + (idx >> p.xform_log);
+      x = Fr::load_nc(in + src * 32);
       if (!p.mont_in) {
         if (!fr_is_canonical(x)) atomicOr(p.flag, 1u);
         x = x.to_mont();
@@ -283,7 +285,14 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
         y = y * Fr::load_nc(reinterpret_cast<const char*>(p.post_scale) + idx * 32);
     }
     if (!p.mont_out) y = y.from_mont();
-    y.store(out + idx * 32);
+    if (FINAL && p.out_win) {
+      const uint64_t b = idx >> p.xform_log, i = idx & ((1ull << p.xform_log) - 1);
+      const uint64_t col = i & ((1ull << p.out_col_bits) - 1);
+      char* dst = reinterpret_cast<char*>(p.out_wins[i >> p.out_col_bits]);
+      y.store(dst + ((b << p.out_col_bits) + col) * 32);
+    } else {
+      y.store(out + idx * 32);
+    }
   }
 }
 
@@ -321,20 +330,7 @@ __global__ void fr_convert_kernel(Fr* data, uint64_t n, int to_mont) {
   x.store(data + i);
 }
 
-// [A][B][C] -> [B][A][C] on 32-byte elements; one thread per 16-byte half for coalescing
-__global__ void fr_permute_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t A,
-                                  uint32_t B, uint32_t C) {
-  uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;     // output half-element index
-  uint64_t total = uint64_t(A) * B * C * 2;
-  if (q >= total) return;
-  uint64_t e = q >> 1;
-  uint32_t c = uint32_t(e % C);
-  uint64_t r = e / C;
-  uint32_t a = uint32_t(r % A), b = uint32_t(r / A);
-  out[q] = in[(((uint64_t(a) * B + b) * C + c) << 1) | (q & 1)];
-}
-
-// layout-d block of rank g out of a natural-order vector (dist_ntt.py):
+// layout-d block of rank g out of a natural-order vector (csrc/dist.cu):
 // out[low_loc * H + high] = full[(g * lows + low_loc) + (high << d)],  H = n >> d
 __global__ void fr_gather_layout_kernel(const uint4* __restrict__ full, uint4* __restrict__ out,
                                         uint32_t log_n, uint32_t d, uint32_t lows, uint32_t low0) {
@@ -401,14 +397,6 @@ void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t 
                                                 reinterpret_cast<const Fr*>(lo),
                                                 reinterpret_cast<const Fr*>(hi), lo_bits, tw_shift,
                                                 s_bits, M);
-  count_launches(blocks ? 1 : 0);
-}
-
-void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32_t C, cudaStream_t s) {
-  uint64_t total = uint64_t(A) * B * C * 2;
-  uint32_t blocks = uint32_t((total + 255) / 256);
-  if (blocks)
-    fr_permute_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), A, B, C);
   count_launches(blocks ? 1 : 0);
 }
 

@@ -29,6 +29,19 @@ struct NttPassArgs {
   uint32_t row_digit_bits[4];
   uint32_t batch_log;      // each transform covers 2^batch_log elements; tiles beyond one transform's
   uint32_t tiles_per_batch;//   count belong to the next transform of a contiguous batch (final mode)
+  // ---- fused exchange of the multi-GPU four-step NTT (dist.cu); both off for ordinary transforms
+  // in_ilv: the FIRST pass reads a batch stored element-major: element i of transform b lives at
+  //   i * batch + b (the layout the all-to-all delivers: [source row][local column]), so the unpack
+  //   permutation is just this pass's load indexing.
+  // out_win: the LAST pass stores element i of transform b to rank (i >> out_col_bits)'s receive
+  //   window at row b, column i & (2^out_col_bits - 1): twiddle, pack and the all-to-all itself are
+  //   this pass's store loop — out_wins[] are peer-mapped (NVLink) or local staging pointers.
+  int in_ilv;
+  uint32_t in_ilv_log;     // log2(batch)
+  int out_win;
+  uint32_t out_col_bits;
+  uint32_t xform_log;      // log2 of the transform size (splits a logical index into (b, i))
+  void* out_wins[16];
   uint32_t* flag;          // bit 0 raised when a canonical-form input (mont_in == 0) is >= r
   int mont_in;             // 0: input is canonical integers, convert while loading
   int mont_out;            // 0: convert the result back to canonical integers while storing
@@ -40,8 +53,6 @@ void fr_powers_launch(void* out, const uint32_t base[8], const uint32_t c[8], ui
 void fr_twiddle_full_launch(void* tab, const void* lo, const void* hi, uint32_t lo_bits,
                             uint32_t tw_shift, uint32_t s_bits, uint64_t M, cudaStream_t s);
 void fr_convert_launch(void* data, uint64_t n, int to_mont, cudaStream_t s);
-// out[(b*A + a)*C + c] = in[(a*B + b)*C + c]  : [A][B][C] -> [B][A][C]   (32-byte elements)
-void fr_permute_launch(const void* in, void* out, uint32_t A, uint32_t B, uint32_t C, cudaStream_t s);
 // index-mapped power tables for the distributed (four-step) NTT, pos = hi * cols + lo:
 //   mode 0: out[pos] = c * base^{(row0 + hi) * lo}            (inter-step twiddle  w^{i2 * k1})
 //   mode 1: out[pos] = c * base^{(row0 + hi) + lo * mul}      (coset powers at global index k1 + N1 k2)

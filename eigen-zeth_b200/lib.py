@@ -17,7 +17,7 @@ VK_BYTES, PROOF_BYTES, INTERMEDIATE_BYTES = 576, 256, 384
 
 EXPORTS = [
     "zkb_version", "zkb_ctx_create", "zkb_ctx_destroy", "zkb_last_error", "zkb_ctx_stream", "zkb_ctx_sync",
-    "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_fr_ntt_batch_dev", "zkb_fr_permute_dev", "zkb_fr_table_dev",
+    "zkb_ctx_set", "zkb_fr_ntt", "zkb_fr_ntt_dev", "zkb_fr_ntt_batch_dev", "zkb_fr_table_dev",
     "zkb_fr_mul_sub_dev", "zkb_fr_convert_dev", "zkb_fr_root_of_unity", "zkb_bases_upload_g1", "zkb_bases_upload_g2",
     "zkb_bases_synthetic_g1", "zkb_bases_synthetic_g2", "zkb_bases_download", "zkb_bases_len", "zkb_bases_free",
     "zkb_bases_precompute", "zkb_bases_window",
@@ -28,7 +28,12 @@ EXPORTS = [
     "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings", "zkb_host_alloc", "zkb_host_free", "zkb_pk_n_vars", "zkb_pk_log_n",
+    "zkb_comm_unique_id", "zkb_comm_init", "zkb_comm_init_local", "zkb_comm_rank", "zkb_comm_world",
+    "zkb_comm_transport", "zkb_comm_barrier", "zkb_comm_destroy", "zkb_fr_ntt_dist_dev",
+    "zkb_fr_index_power_table_dist", "zkb_msm_g1_dist_dev", "zkb_msm_g2_dist_dev", "zkb_msm_g1_dist",
+    "zkb_msm_g2_dist", "zkb_pk_synthetic_dist", "zkb_groth16_prove_dist",
 ]
+COMM_ID_BYTES = 128
 
 
 class ZkbError(RuntimeError):
@@ -88,7 +93,6 @@ def load_library() -> C.CDLL:
     lib.zkb_fr_ntt.argtypes = [vp, vp, u32, i32, i32]
     lib.zkb_fr_ntt_dev.argtypes = [vp, vp, vp, u32, i32, i32, i32]
     lib.zkb_fr_ntt_batch_dev.argtypes = [vp, vp, vp, u32, u64, i32, i32, vp, vp]
-    lib.zkb_fr_permute_dev.argtypes = [vp, vp, vp, u32, u32, u32]
     lib.zkb_fr_table_dev.argtypes = [vp, vp, u8p, u8p, u64, u64, u64, u64, i32]
     lib.zkb_fr_mul_sub_dev.argtypes = [vp, vp, vp, vp, u64]
     lib.zkb_fr_convert_dev.argtypes = [vp, vp, u64, i32]
@@ -130,6 +134,20 @@ def load_library() -> C.CDLL:
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
         lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
+    lib.zkb_comm_unique_id.argtypes = [vp]
+    lib.zkb_comm_init.argtypes = [vp, u8p, i32, i32]
+    lib.zkb_comm_init_local.argtypes = [C.POINTER(vp), i32]
+    for name in ("zkb_comm_rank", "zkb_comm_world", "zkb_comm_transport", "zkb_comm_barrier"):
+        getattr(lib, name).argtypes = [vp]
+    lib.zkb_comm_destroy.argtypes = [vp]
+    lib.zkb_comm_destroy.restype = None
+    lib.zkb_fr_ntt_dist_dev.argtypes = [vp, vp, u32, u32, i32, vp, vp]
+    lib.zkb_fr_index_power_table_dist.argtypes = [vp, u32, u32, u8p, u8p, C.POINTER(vp)]
+    for g in ("g1", "g2"):
+        getattr(lib, "zkb_msm_%s_dist_dev" % g).argtypes = [vp, vp, u64, vp, u64, vp]
+        getattr(lib, "zkb_msm_%s_dist" % g).argtypes = [vp, vp, u64, vp, u64, vp]
+    lib.zkb_pk_synthetic_dist.argtypes = [vp, u32, u64, C.POINTER(vp), vp]
+    lib.zkb_groth16_prove_dist.argtypes = [vp, vp, vp, u8p, u8p, vp, C.POINTER(ProveTimings)]
     lib.zkb_r1cs_inspect.argtypes = [u8p, u64, C.POINTER(R1csInfo)]
     lib.zkb_r1cs_read.argtypes = [u8p, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.zkb_wtns_inspect.argtypes = [u8p, u64, C.POINTER(u32)]
@@ -282,9 +300,6 @@ class Context:
     def fr_ntt_batch_dev(self, d_in, d_out, log_size, batch, inverse=False, skip_ninv=False, pre=0, post=0):
         self._check(self.lib.zkb_fr_ntt_batch_dev(self.h, d_in, d_out, log_size, batch, int(inverse), int(skip_ninv),
                                                   pre or None, post or None))
-
-    def fr_permute_dev(self, d_in, d_out, a, b, c):
-        self._check(self.lib.zkb_fr_permute_dev(self.h, d_in, d_out, a, b, c))
 
     def fr_table_dev(self, d_out, base: bytes, scale: bytes, rows, cols, row0, mul, mode):
         self._check(self.lib.zkb_fr_table_dev(self.h, d_out, base, scale, rows, cols, row0, mul, mode))
@@ -449,6 +464,63 @@ class Context:
         self._check(self.lib.zkb_groth16_prove(self.h, pk.handle, wptr, r, s, proof, inter, hbuf, C.byref(t)))
         return proof.raw, (inter.raw if inter else None), (hbuf.raw if hbuf else None), t.as_dict()
 
+    # ---- several GPUs: collective calls over this context's communicator
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """join an NCCL communicator (one process or thread per rank); collective"""
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique id must be %d bytes" % COMM_ID_BYTES)
+        self._check(self.lib.zkb_comm_init(self.h, bytes(unique_id), rank, world))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(self.lib.zkb_comm_rank(self.h))
+
+    @property
+    def comm_world(self) -> int:
+        return int(self.lib.zkb_comm_world(self.h))
+
+    @property
+    def comm_transport(self) -> str:
+        return {0: "none", 1: "peer-memory windows (NVLink stores from the NTT epilogue)",
+                2: "NCCL send/recv staging"}[int(self.lib.zkb_comm_transport(self.h))]
+
+    def comm_barrier(self):
+        self._check(self.lib.zkb_comm_barrier(self.h))
+
+    def fr_ntt_dist_dev(self, d_data: int, log_n: int, low_bits: int, inverse=False, pre=0, post=0):
+        self._check(self.lib.zkb_fr_ntt_dist_dev(self.h, d_data, log_n, low_bits, int(inverse), pre or None, post or None))
+
+    def fr_index_power_table_dist(self, log_n: int, low_bits: int, base: int, scale: int = 1) -> int:
+        out = C.c_void_p()
+        from .proof_format import R
+        self._check(self.lib.zkb_fr_index_power_table_dist(self.h, log_n, low_bits, (base % R).to_bytes(32, "little"),
+                                                           (scale % R).to_bytes(32, "little"), C.byref(out)))
+        return int(out.value)
+
+    def msm_dist_dev(self, bases: Bases, d_scalars: int, n: int, d_out: int, first=0):
+        fn = self.lib.zkb_msm_g2_dist_dev if bases.g2 else self.lib.zkb_msm_g1_dist_dev
+        self._check(fn(self.h, bases.handle, first, d_scalars, n, d_out))
+
+    def msm_dist_raw(self, bases: Bases, host_ptr: int, n: int, first=0) -> bytes:
+        out = C.create_string_buffer(128 if bases.g2 else 64)
+        fn = self.lib.zkb_msm_g2_dist if bases.g2 else self.lib.zkb_msm_g1_dist
+        self._check(fn(self.h, bases.handle, first, host_ptr, n, out))
+        return out.raw
+
+    def pk_synthetic_dist(self, log_n: int, seed: int) -> ProvingKey:
+        h = C.c_void_p()
+        vk = C.create_string_buffer(VK_BYTES)
+        self._check(self.lib.zkb_pk_synthetic_dist(self.h, log_n, seed, C.byref(h), vk))
+        return ProvingKey(self, h, vk.raw, log_n)
+
+    def groth16_prove_dist(self, pk: ProvingKey, witness, r: bytes, s: bytes):
+        """collective: every rank calls it with the same witness; -> (proof, timings)"""
+        proof = C.create_string_buffer(PROOF_BYTES)
+        t = ProveTimings()
+        wptr, _keep = pk.witness_ptr(witness)
+        self._check(self.lib.zkb_groth16_prove_dist(self.h, pk.handle, wptr, r, s, proof, C.byref(t)))
+        return proof.raw, t.as_dict()
+
     # ---- hooks
     def field_op(self, field: int, op: int, a: bytes, b: bytes | None = None) -> bytes:
         n = len(a) // 32
@@ -467,6 +539,61 @@ class Context:
         res = (C.c_double * 3)()
         self._check(self.lib.zkb_bench_int_pipe(self.h, iters, res))
         return {"imad_wide_per_s": res[0], "montmul_per_s": res[1], "sm_mhz": res[2]}
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id for Context.comm_init (made by rank 0, handed to the other ranks)"""
+    out = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load_library().zkb_comm_unique_id(out)
+    if rc:
+        raise ZkbError(rc, "zkb_comm_unique_id failed (is libnccl.so.2 loadable?)")
+    return out.raw
+
+
+class DeviceGroup:
+    """All ranks of a communicator inside ONE process: one context and one host thread per GPU
+    (zkb_comm_init_local: peer pointers + CUDA events, no NCCL).  This is how the prover service
+    spreads one GenFinalProof over the GPUs of a box.  `devices` may repeat a device (tests on a
+    single GPU)."""
+
+    def __init__(self, devices):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = list(devices)
+        self.world = len(self.devices)
+        self.ctxs = [Context(d) for d in self.devices]
+        arr = (C.c_void_p * self.world)(*[c.h for c in self.ctxs])
+        rc = load_library().zkb_comm_init_local(arr, self.world)
+        if rc:
+            raise ZkbError(rc, "zkb_comm_init_local failed (world must be a power of two <= 16; GPUs need peer access)")
+        self.pool = [ThreadPoolExecutor(max_workers=1) for _ in self.devices]     # one thread per rank, for life
+        self.pks, self.vk = None, None
+
+    def run(self, fn):
+        """fn(rank, ctx) on every rank concurrently (ctypes releases the GIL inside the library)"""
+        futs = [self.pool[r].submit(fn, r, self.ctxs[r]) for r in range(self.world)]
+        return [f.result() for f in futs]
+
+    def pk_synthetic(self, log_n: int, seed: int):
+        self.pks = self.run(lambda r, ctx: ctx.pk_synthetic_dist(log_n, seed))
+        self.vk = self.pks[0].vk
+        return self.pks
+
+    def groth16_prove(self, witness, r: bytes, s: bytes):
+        """one proof over all GPUs of the group -> (proof, timings of the slowest rank)"""
+        out = self.run(lambda k, ctx: ctx.groth16_prove_dist(self.pks[k], witness, r, s))
+        proofs = {p for p, _ in out}
+        if len(proofs) != 1:
+            raise RuntimeError("ranks disagree on the proof")
+        return out[0][0], max((t for _, t in out), key=lambda t: t["ms_total"])
+
+    def close(self):
+        for p in self.pool:
+            p.shutdown(wait=True)
+        if self.pks:
+            for pk in self.pks:
+                pk.free()
+        for c in self.ctxs:
+            c.close()
 
 
 def host_alloc(nbytes: int) -> int:

@@ -54,7 +54,9 @@ const char* zkb_last_error(const zkb_ctx* ctx);
 void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
 /* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1),
- * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys) */
+ * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys),
+ * "msm_g2_pair" (process-wide, default 1: the G2 bucket walk splits each Fq2 point operation over a
+ * lane pair; 0 = the one-thread-per-point walk, kept for comparison) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
 /* page-locked (pinned, portable) host memory for witnesses / scalars: H2D copies from it run at PCIe
@@ -70,19 +72,17 @@ int zkb_fr_ntt(zkb_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, int cos
 int zkb_fr_ntt_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inverse,
                    int coset, int montgomery);
 
-/* Building blocks of the multi-GPU four-step NTT (one process per GPU; the transpose between the
- * two steps is an NCCL all-to-all issued above this layer, eigen-zeth_b200/dist_ntt.py).  Device
- * buffers, Montgomery form, asynchronous on the ctx stream.
+/* Batched / table building blocks (the multi-GPU four-step NTT itself is zkb_fr_ntt_dist_dev below;
+ * eigen-zeth_b200/dist_ntt.py composes the same steps above this layer for the emulated-rank
+ * tests).  Device buffers, Montgomery form, asynchronous on the ctx stream.
  *  - `batch` contiguous transforms of 2^log_size elements; tables (optional, batch * 2^log_size
  *    entries, Montgomery) multiply the input / output element-wise; skip_ninv leaves 1/size out;
- *  - permute: [a][b][c] -> [b][a][c] on 32-byte elements;
  *  - table mode 0: out[hi*cols+lo] = scale * base^((row0+hi)*lo); mode 1: scale * base^((row0+hi) + lo*mul)
  *    (base, scale canonical; output Montgomery);
  *  - mul_sub: a[i] = a[i]*b[i] - c[i];   convert: canonical <-> Montgomery in place. */
 int zkb_fr_ntt_batch_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_size, uint64_t batch,
                          int inverse, int skip_ninv, const void* d_pre_table, const void* d_post_table);
-int zkb_fr_permute_dev(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t a, uint32_t b, uint32_t c);
-/* this rank's layout-d block of a natural-order device vector (dist_ntt.py "layout d") */
+/* this rank's block of "layout low_bits" (see zkb_fr_ntt_dist_dev) out of a natural-order device vector */
 int zkb_fr_gather_layout_dev(zkb_ctx* ctx, const void* d_full, void* d_out, uint32_t log_n, uint32_t low_bits,
                              uint32_t world, uint32_t rank);
 int zkb_fr_table_dev(zkb_ctx* ctx, void* d_out, const uint8_t base[32], const uint8_t scale[32], uint64_t rows,
@@ -126,6 +126,54 @@ int zkb_g2_sum(zkb_ctx* ctx, const uint8_t* points, uint32_t n, uint8_t out[128]
 /* the same on device buffers (e.g. the output of an NCCL all-gather), asynchronous */
 int zkb_g1_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out);
 int zkb_g2_sum_dev(zkb_ctx* ctx, const void* d_points, uint32_t n, void* d_out);
+
+/* ---- several GPUs  (BASELINE.json configs[3], configs[4]) ------------------------
+ * The reference has no distributed backend: its operator knows ONE prover address
+ * (src/config/env.rs:21, scripts/start-l2.sh:3).  Behind that address one proof can be spread over
+ * the GPUs of a box: one zkb_ctx per GPU, joined into a communicator, and the zkb_*_dist calls are
+ * COLLECTIVE — every rank calls them, in the same order, from its own host thread or process.
+ *  - zkb_comm_init: one process (or thread) per rank; rendezvous through NCCL (libnccl.so.2 is
+ *    loaded at this call, not before): rank 0 makes an id with zkb_comm_unique_id and hands it to
+ *    the others by any means (file, socket, torch.distributed);
+ *  - zkb_comm_init_local: all ranks inside ONE process (the prover service: one host thread per
+ *    GPU); no NCCL at all — peer pointers and CUDA events.  Contexts may share a device (tests).
+ * world must be a power of two <= 16.
+ * The exchange of the four-step NTT is fused into the NTT kernels: the last pass of the first step
+ * stores each element straight into the destination rank's receive window (peer memory over
+ * NVLink; CUDA IPC between processes), the first pass of the second step reads the window
+ * transposed.  zkb_comm_transport: 1 = those peer-memory windows, 2 = NCCL send/recv staging
+ * (fallback when peer mapping is refused), 0 = no exchange has run yet. */
+#define ZKB_COMM_ID_BYTES 128
+int zkb_comm_unique_id(uint8_t id_out[ZKB_COMM_ID_BYTES]);
+int zkb_comm_init(zkb_ctx* ctx, const uint8_t id[ZKB_COMM_ID_BYTES], int rank, int world);
+int zkb_comm_init_local(zkb_ctx* const* ctxs, int world);
+int zkb_comm_rank(const zkb_ctx* ctx);
+int zkb_comm_world(const zkb_ctx* ctx);
+int zkb_comm_transport(const zkb_ctx* ctx);
+int zkb_comm_barrier(zkb_ctx* ctx);                 /* stream-ordered barrier over the ranks */
+void zkb_comm_destroy(zkb_ctx* ctx);
+/* One four-step transform of a length-2^log_n vector held in "layout low_bits": index = low +
+ * 2^low_bits * high, rank g owns the lows [g * 2^low_bits / world, (g+1) * 2^low_bits / world) and
+ * all highs, local array [low_loc][high] (2^log_n / world elements, Montgomery form, device).
+ * In place; the result is in layout log_n - low_bits, natural NTT order (ark-poly semantics, an
+ * inverse carries 1/n).  Tables (optional, device, Montgomery, 2^log_n / world entries) multiply
+ * the input / output element-wise in the input / output layout. */
+int zkb_fr_ntt_dist_dev(zkb_ctx* ctx, void* d_data, uint32_t log_n, uint32_t low_bits, int inverse,
+                        const void* d_pre_table, const void* d_post_table);
+/* table[pos] = scale * base^(global index of pos) for this rank's block of layout low_bits (coset
+ * shifts); built once, cached and owned by the context */
+int zkb_fr_index_power_table_dist(zkb_ctx* ctx, uint32_t log_n, uint32_t low_bits, const uint8_t base[32],
+                                  const uint8_t scale[32], const void** d_table_out);
+/* MSM sharded by point range: every rank passes ITS bases and scalars, every rank receives the
+ * total.  The only exchange is an all-gather of one affine point per rank. */
+int zkb_msm_g1_dist_dev(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars,
+                        uint64_t n, void* d_out);
+int zkb_msm_g2_dist_dev(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_scalars,
+                        uint64_t n, void* d_out);
+int zkb_msm_g1_dist(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,
+                    uint64_t n, uint8_t out[64]);
+int zkb_msm_g2_dist(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* scalars,
+                    uint64_t n, uint8_t out[128]);
 
 /* ---- Groth16  (GenFinalProofRequest -> FinalProof; prover.proto:130-148) --------------------- */
 /* verifying key layout: alpha_g1 64 | beta_g2 128 | gamma_g2 128 | delta_g2 128 | ic0 64 | ic1 64 */
@@ -206,6 +254,18 @@ int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
                         uint8_t partial_out[ZKB_INTERMEDIATE_BYTES]);
 int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
                          const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES]);
+/* One proof over all ranks of ctx's communicator (collective).  The key holds this rank's point
+ * range of every query, h_query in the layout the last four-step transform produces; every rank
+ * passes the same full witness (host pointer: each uploads 1/world of it over PCIe and the slices
+ * are all-gathered over NVLink; or a device pointer) and every rank receives the proof.  Witness
+ * map: 7 four-step NTTs; MSMs: sharded by point range; the 384-byte partial sums are gathered,
+ * added and assembled on the device.  timings: ms_h2d = witness staging, ms_spmv, ms_ntt,
+ * ms_msm_a = the four witness MSMs (one shared sort), ms_msm_h, ms_total. */
+int zkb_pk_synthetic_dist(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
+                          uint8_t vk_out[ZKB_VK_BYTES]);
+int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
+                           const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
+                           zkb_prove_timings* timings_opt);
 /* CPU pairing check e(A,B) = e(alpha,beta) e(ic0 + x*ic1, gamma) e(C,delta); 0 = valid,
  * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
 int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],

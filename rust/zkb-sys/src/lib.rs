@@ -23,6 +23,7 @@ pub const ZKB_ECOMM: c_int = -7;
 pub const ZKB_VK_BYTES: usize = 576;
 pub const ZKB_PROOF_BYTES: usize = 256;
 pub const ZKB_INTERMEDIATE_BYTES: usize = 384;
+pub const ZKB_COMM_ID_BYTES: usize = 128;
 // reason bits of zkb_proof_check
 pub const ZKB_BAD_A_RANGE: u32 = 0x001;
 pub const ZKB_BAD_A_CURVE: u32 = 0x002;
@@ -80,7 +81,6 @@ extern "C" {
     pub fn zkb_fr_ntt(ctx: *mut zkb_ctx, data: *mut u8, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
     pub fn zkb_fr_ntt_dev(ctx: *mut zkb_ctx, d_in: *const c_void, d_out: *mut c_void, log_n: u32, inverse: c_int, coset: c_int, montgomery: c_int) -> c_int;
     pub fn zkb_fr_ntt_batch_dev(ctx: *mut zkb_ctx, d_in: *const c_void, d_out: *mut c_void, log_size: u32, batch: u64, inverse: c_int, skip_ninv: c_int, d_pre_table: *const c_void, d_post_table: *const c_void) -> c_int;
-    pub fn zkb_fr_permute_dev(ctx: *mut zkb_ctx, d_in: *const c_void, d_out: *mut c_void, a: u32, b: u32, c: u32) -> c_int;
     pub fn zkb_fr_gather_layout_dev(ctx: *mut zkb_ctx, d_full: *const c_void, d_out: *mut c_void, log_n: u32, low_bits: u32, world: u32, rank: u32) -> c_int;
     pub fn zkb_fr_table_dev(ctx: *mut zkb_ctx, d_out: *mut c_void, base: *const u8, scale: *const u8, rows: u64, cols: u64, row0: u64, mul: u64, mode: c_int) -> c_int;
     pub fn zkb_fr_mul_sub_dev(ctx: *mut zkb_ctx, d_a: *mut c_void, d_b: *const c_void, d_c: *const c_void, n: u64) -> c_int;
@@ -103,6 +103,20 @@ extern "C" {
     pub fn zkb_g2_sum(ctx: *mut zkb_ctx, points: *const u8, n: u32, out_: *mut u8) -> c_int;
     pub fn zkb_g1_sum_dev(ctx: *mut zkb_ctx, d_points: *const c_void, n: u32, d_out: *mut c_void) -> c_int;
     pub fn zkb_g2_sum_dev(ctx: *mut zkb_ctx, d_points: *const c_void, n: u32, d_out: *mut c_void) -> c_int;
+    pub fn zkb_comm_unique_id(id_out: *mut u8) -> c_int;
+    pub fn zkb_comm_init(ctx: *mut zkb_ctx, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn zkb_comm_init_local(ctxs: *mut *mut zkb_ctx, world: c_int) -> c_int;
+    pub fn zkb_comm_rank(ctx: *const zkb_ctx) -> c_int;
+    pub fn zkb_comm_world(ctx: *const zkb_ctx) -> c_int;
+    pub fn zkb_comm_transport(ctx: *const zkb_ctx) -> c_int;
+    pub fn zkb_comm_barrier(ctx: *mut zkb_ctx) -> c_int;
+    pub fn zkb_comm_destroy(ctx: *mut zkb_ctx);
+    pub fn zkb_fr_ntt_dist_dev(ctx: *mut zkb_ctx, d_data: *mut c_void, log_n: u32, low_bits: u32, inverse: c_int, d_pre_table: *const c_void, d_post_table: *const c_void) -> c_int;
+    pub fn zkb_fr_index_power_table_dist(ctx: *mut zkb_ctx, log_n: u32, low_bits: u32, base: *const u8, scale: *const u8, d_table_out: *const *mut c_void) -> c_int;
+    pub fn zkb_msm_g1_dist_dev(ctx: *mut zkb_ctx, b: *const zkb_bases, first: u64, d_scalars: *const c_void, n: u64, d_out: *mut c_void) -> c_int;
+    pub fn zkb_msm_g2_dist_dev(ctx: *mut zkb_ctx, b: *const zkb_bases, first: u64, d_scalars: *const c_void, n: u64, d_out: *mut c_void) -> c_int;
+    pub fn zkb_msm_g1_dist(ctx: *mut zkb_ctx, b: *const zkb_bases, first: u64, scalars: *const u8, n: u64, out_: *mut u8) -> c_int;
+    pub fn zkb_msm_g2_dist(ctx: *mut zkb_ctx, b: *const zkb_bases, first: u64, scalars: *const u8, n: u64, out_: *mut u8) -> c_int;
     pub fn zkb_pk_synthetic(ctx: *mut zkb_ctx, log_n: u32, seed: u64, out_: *mut *mut zkb_pk, vk_out: *mut u8) -> c_int;
     pub fn zkb_pk_synthetic_shard(ctx: *mut zkb_ctx, log_n: u32, seed: u64, rank: u32, world: u32, out_: *mut *mut zkb_pk, vk_out: *mut u8) -> c_int;
     pub fn zkb_pk_load(ctx: *mut zkb_ctx, desc: *const zkb_pk_desc, out_: *mut *mut zkb_pk) -> c_int;
@@ -118,6 +132,8 @@ extern "C" {
     pub fn zkb_groth16_witness_layout_dev(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, low_bits: u32, world: u32, rank: u32, d_abc_local: *mut *mut c_void) -> c_int;
     pub fn zkb_groth16_msm_dev(ctx: *mut zkb_ctx, pk: *const zkb_pk, d_h: *const c_void, partial_out: *mut u8) -> c_int;
     pub fn zkb_groth16_assemble(ctx: *mut zkb_ctx, pk: *const zkb_pk, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
+    pub fn zkb_pk_synthetic_dist(ctx: *mut zkb_ctx, log_n: u32, seed: u64, out_: *mut *mut zkb_pk, vk_out: *mut u8) -> c_int;
+    pub fn zkb_groth16_prove_dist(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8, timings_opt: *mut zkb_prove_timings) -> c_int;
     pub fn zkb_groth16_verify(vk: *const u8, proof: *const u8, public_input: *const u8) -> c_int;
     pub fn zkb_proof_check(proof: *const u8, public_input: *const u8, reasons_opt: *mut u32) -> c_int;
     pub fn zkb_r1cs_inspect(file: *const u8, len: u64, out_: *mut zkb_r1cs_info) -> c_int;

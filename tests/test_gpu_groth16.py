@@ -158,8 +158,17 @@ def test_pk_load_external_circuit(ctx, zkb, log_n):
     assert h == oh and inter == ointer and proof == oproof
     assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])
     # error behaviour: inconsistent dimensions / out-of-range column / non-canonical coefficient
-    with pytest.raises(zkb.ZkbError):
+    with pytest.raises((zkb.ZkbError, ValueError)):     # the binding already rejects the short h_query
         ctx.pk_load(log_n - 1, cs["m"], cs["n_pub"], mats, queries, opk.fixed())
+    short = dict(queries, a_query=queries["a_query"][:-64])
+    with pytest.raises(ValueError, match="a_query"):
+        ctx.pk_load(log_n, cs["m"], cs["n_pub"], mats, short, opk.fixed())
+    off = bytearray(queries["a_query"])
+    off[0] ^= 1                                          # x changed: the point leaves the curve
+    with pytest.raises(zkb.ZkbError, match="not on the curve"):
+        ctx.pk_load(log_n, cs["m"], cs["n_pub"], mats, dict(queries, a_query=bytes(off)), opk.fixed())
+    with pytest.raises(ValueError, match="witness holds"):
+        ctx.groth16_prove(pk, wit[:-32], r, s)
     bad = [(mats[0][0], [cs["m"]] + mats[0][1][1:], mats[0][2]), mats[1], mats[2]]
     with pytest.raises(zkb.ZkbError):
         ctx.pk_load(log_n, cs["m"], cs["n_pub"], bad, queries, opk.fixed())

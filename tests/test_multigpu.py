@@ -1,5 +1,6 @@
-"""Real NCCL paths (four-step NTT all-to-all, sharded Groth16): needs >= 2 visible GPUs, otherwise
-skipped — the same logic is covered with emulated ranks in test_gpu_dist_ntt.py / test_gpu_groth16.py."""
+"""The NCCL transport between PROCESSES (zkb_comm_init + CUDA-IPC receive windows, and the
+ncclSend/ncclRecv staging fallback): needs >= 2 visible GPUs, otherwise skipped — the same library
+code runs with emulated ranks in tests/test_gpu_dist.py."""
 import os
 import subprocess
 import sys
@@ -10,31 +11,38 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_nccl_paths_match_single_gpu():
+@pytest.mark.parametrize("staging", [0, 1])
+def test_nccl_paths_match_single_gpu(staging):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 1 << (n.bit_length() - 1)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "--master-addr", "127.0.0.1", "--master-port", str(29533 + staging), os.path.join(ROOT, "tools", "dist_check.py")]
+    env = dict(os.environ, ZKB_FORCE_STAGING=str(staging))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "MULTIGPU OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_four_step_prover_world1_equals_standard_prove(ctx, zkb):
-    """the distributed witness-map chain with a single rank (no collective) must reproduce the
-    standard prover bit for bit — this pins the layout bookkeeping and the folded tables."""
-    from eigen_zeth_b200.sharding import FourStepProver
-    for log_n in (6, 9, 12, 16):
-        seed = 0x5EED0004 + log_n
-        w = zkb.synthetic_witness(log_n, (3).to_bytes(32, "little"), (9).to_bytes(32, "little"))
-        r, s = (21).to_bytes(32, "little"), (34).to_bytes(32, "little")
-        pk = ctx.pk_synthetic(log_n, seed)
-        want, _, h_want, _ = ctx.groth16_prove(pk, w, r, s, want_h=True)
-        prover = FourStepProver(ctx, log_n, 1, 0)
-        fpk = ctx.pk_synthetic_shard(log_n, seed, 0, 1, h_low_bits=prover.h_low_bits)
-        assert prover.prove(fpk, w, r, s) == want
-        assert zkb.groth16_verify(pk.vk, want, w[32:64])
-        pk.free()
-        fpk.free()
+def test_device_group_on_all_visible_gpus(zkb):
+    """zkb_comm_init_local across real devices (the prover service's --devices mode): peer pointers
+    over NVLink, no NCCL"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 1 << (n.bit_length() - 1)
+    group = zkb.lib.DeviceGroup(list(range(world)))
+    log_n, seed = 16, 0x5EED0004
+    w = zkb.synthetic_witness(log_n, (5).to_bytes(32, "little"), (7).to_bytes(32, "little"))
+    r, s = (11).to_bytes(32, "little"), (13).to_bytes(32, "little")
+    group.pk_synthetic(log_n, seed)
+    proof, _ = group.groth16_prove(w, r, s)
+    c0 = zkb.Context(0)
+    pk = c0.pk_synthetic(log_n, seed)
+    want, _, _, _ = c0.groth16_prove(pk, w, r, s)
+    assert proof == want and zkb.groth16_verify(pk.vk, proof, w[32:64])
+    pk.free()
+    c0.close()
+    group.close()

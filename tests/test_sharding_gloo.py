@@ -68,12 +68,12 @@ def test_sharded_msm_world2_gloo():
 
 # ---------------------------------------------------------------- four-step NTT layout algebra over gloo
 def _four_step_worker(rank, world, port, log_n, q):
-    """the five steps of dist_ntt.FourStepNtt with Python-int math for the local transforms and a
+    """the steps of the four-step NTT (csrc/dist.cu) with Python-int math for the local transforms and a
     real process group for the exchange (gloo has no all_to_all, so it is built from all_gather)."""
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_a as o
-    from eigen_zeth_b200.dist_ntt import local_index_map
+    from eigen_zeth_b200.sharding import local_index_map
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n, d = 1 << log_n, log_n // 2
@@ -83,7 +83,7 @@ def _four_step_worker(rank, world, port, log_n, q):
     full = [rng.fr() for _ in range(n)]
     want = o.ntt(full)
     idx_in = local_index_map(log_n, d, world, rank)              # [low_loc][high] -> global index
-    x = [[full[int(idx_in[l, h])] for h in range(N1)] for l in range(mloc)]
+    x = [[full[idx_in[l][h]] for h in range(N1)] for l in range(mloc)]
     w = o.fr_root_of_unity(log_n)
     # (a) size-N1 transforms over `high`, then the inter-step twiddle w^{i2 * k1}
     y = []
@@ -102,7 +102,7 @@ def _four_step_worker(rank, world, port, log_n, q):
     for k in range(n1loc):
         out.append(o.ntt([flat[i2 * n1loc + k] for i2 in range(M)]))
     idx_out = local_index_map(log_n, log_n - d, world, rank)     # layout L-d of the result
-    ok = all(out[l][h] == want[int(idx_out[l, h])] for l in range(n1loc) for h in range(M))
+    ok = all(out[l][h] == want[idx_out[l][h]] for l in range(n1loc) for h in range(M))
     q.put((rank, ok))
     dist.destroy_process_group()
 
