@@ -463,7 +463,7 @@ def extras(args, line, ctx, z, ob, torch, dist, dev, stream, world, rank, barrie
         else:
             n_loc = n // world
             blk = torch.from_numpy(uniform_fr_scalars(n_loc, 99 + rank).view("int64")).to(dev)
-            d = log_n // 2
+            d = min(8, log_n // 2)      # one single-pass batch of 2^8 + one multi-pass batch: as many passes as on one GPU
             # layout d -> layout log_n - d -> layout d: two transforms per call keep the layout fixed
             t_ms = timed(lambda: (ctx.fr_ntt_dist_dev(blk.data_ptr(), log_n, d), ctx.fr_ntt_dist_dev(blk.data_ptr(), log_n, log_n - d)), steps) / 2
             line["ntt_2^%d_four_step" % log_n] = {

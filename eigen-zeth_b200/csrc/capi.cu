@@ -272,7 +272,13 @@ int ntt_run(zkb_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, int inv
     uint32_t tiles = ((k0_range + CT - 1) / CT) << (a.row_bits - a.first_digit_bits);
     a.batch_log = log_n;
     a.tiles_per_batch = batch > 1 ? tiles : 0;
-    ntt_launch_pass(a, true, uint32_t(tiles * batch), ctx->stream);
+    uint64_t n_tiles = uint64_t(tiles) * batch;
+    if (P == 1 && batch > 1) {          // columns of a tile = consecutive transforms of the batch
+      a.batch_cols = 1;
+      a.batch_count = uint32_t(batch);
+      n_tiles = (batch + CT - 1) / CT;
+    }
+    ntt_launch_pass(a, true, uint32_t(n_tiles), ctx->stream);
   }
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
@@ -411,6 +417,70 @@ int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* 
     }
     if (ev_opt) cudaEventRecord(ev_opt[j], ctx->stream);
   }
+  ZKB_CUDA(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+// The MSM phase of one Groth16 proof.  qs = a, b_g1, l (G1) and b_g2 (G2) over the witness z (one
+// digit extraction + one sort for the four of them), h_query over h.  When every G1 query carries
+// window multiples of one width, the four G1 walks fill four bucket sets that ONE tail reduces (the
+// tail is a chain of short latency-bound launches: run four times it costs four times as much, run
+// once over four sets it costs the same as for one).  res: msm_a 64 | msm_b1 64 | msm_b2 128 | msm_l 64 | msm_h 64.
+int msm_exec_prove(zkb_ctx* ctx, const zkb_bases* a, const zkb_bases* b1, const zkb_bases* l, const zkb_bases* b2,
+                   const zkb_bases* h, const void* d_z, uint64_t nz, const void* d_h, uint64_t nh, void* d_res,
+                   cudaEvent_t* ev4_opt) {
+  // ev4_opt (optional): recorded after the a, b_g1, l and b_g2 walks
+  char* res = (char*)d_res;
+  const bool batched = a->precomp_c && a->precomp_c == b1->precomp_c && a->precomp_c == l->precomp_c &&
+                       a->precomp_c == b2->precomp_c && a->precomp_c == h->precomp_c && a->n == b1->n &&
+                       a->n == l->n && a->n == b2->n && nz && nh;
+  if (!batched) {
+    const zkb_bases* qs[4] = {a, b1, l, b2};
+    void* outs4[4] = {res, res + 64, res + 256, res + 128};
+    cudaEvent_t evs[4];
+    if (ev4_opt) { evs[0] = ev4_opt[0]; evs[1] = ev4_opt[1]; evs[2] = ev4_opt[2]; evs[3] = ev4_opt[3]; }
+    int rc = msm_exec_multi(ctx, qs, 4, d_z, 0, nz, outs4, ev4_opt ? evs : nullptr);
+    if (rc) return rc;
+    return msm_exec(ctx, h, 0, d_h, nh, res + 320);
+  }
+  int rc;
+  const zkb_bases* all[5] = {a, b1, l, b2, h};
+  for (int j = 0; j < 5; j++)
+    if ((rc = msm_prepare(ctx, all[j], 0, j == 4 ? nh : nz))) return rc;
+  const int c = a->precomp_c;
+  MsmPlan p1 = msm_make_plan(nz, 0, c, ctx->sm_count, a->n);
+  MsmPlan p2 = msm_make_plan(nz, 1, c, ctx->sm_count, b2->n);
+  MsmPlan ph = msm_make_plan(nh, 0, c, ctx->sm_count, h->n);
+  MsmPlan pt = p1;                         // the shared tail: four independent bucket sets
+  pt.n_sets = 4;
+  pt.n_buckets = 4ull * p1.half;
+  pt.red_run_total = 4 * p1.red_run_total;
+  MsmBuffers buf;
+  if ((rc = ensure_msm_buffers(ctx, p2, &buf))) return rc;
+  if ((rc = ensure_msm_buffers(ctx, ph, &buf))) return rc;
+  if ((rc = ensure_msm_buffers(ctx, p1, &buf))) return rc;
+  if ((rc = ensure_msm_buffers(ctx, pt, &buf, false))) return rc;
+  ZKB_CUDA(ctx, ctx->msm.buckets2.ensure(p2.n_buckets * p2.point_bytes));
+  cudaStream_t st = ctx->stream;
+  char* g1b = (char*)buf.buckets;
+  const size_t set_bytes = size_t(p1.half) * p1.point_bytes;
+  msm_digits_and_sort(p1, buf, d_z, nz, 0, st);
+  msm_accumulate_g1(p1, buf, a->d_pts, g1b, st);
+  if (ev4_opt) cudaEventRecord(ev4_opt[0], st);
+  msm_accumulate_g1(p1, buf, b1->d_pts, g1b + set_bytes, st);
+  if (ev4_opt) cudaEventRecord(ev4_opt[1], st);
+  msm_accumulate_g1(p1, buf, l->d_pts, g1b + 2 * set_bytes, st);
+  if (ev4_opt) cudaEventRecord(ev4_opt[2], st);
+  msm_accumulate_g2(p2, buf, b2->d_pts, ctx->msm.buckets2.p, st);
+  if (ev4_opt) cudaEventRecord(ev4_opt[3], st);
+  msm_digits_and_sort(ph, buf, d_h, nh, 0, st);
+  msm_accumulate_g1(ph, buf, h->d_pts, g1b + 3 * set_bytes, st);
+  void* outs[4] = {res, res + 64, res + 256, res + 320};
+  msm_tail_multi_g1(pt, buf, outs, 4, st);
+  MsmBuffers buf2 = buf;
+  buf2.buckets = ctx->msm.buckets2.p;
+  buf2.result_affine = res + 128;
+  msm_tail_g2(p2, buf2, st);
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }

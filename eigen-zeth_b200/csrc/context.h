@@ -136,6 +136,9 @@ int msm_exec(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const void* d_sca
              void* d_out_affine);
 int msm_exec_multi(zkb_ctx* ctx, const zkb_bases* const* bs, int k, const void* d_scalars, uint64_t first,
                    uint64_t n, void* const* d_outs, cudaEvent_t* ev_opt);
+int msm_exec_prove(zkb_ctx* ctx, const zkb_bases* a, const zkb_bases* b1, const zkb_bases* l, const zkb_bases* b2,
+                   const zkb_bases* h, const void* d_z, uint64_t nz, const void* d_h, uint64_t nh, void* d_res,
+                   cudaEvent_t* ev4_opt);
 // host scalars: H2D in chunks on the copy stream, overlapped with the per-chunk MSM front half
 int msm_exec_host(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, const uint8_t* h_scalars,
                   uint64_t n, void* d_out_affine);

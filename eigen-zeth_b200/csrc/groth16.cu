@@ -715,16 +715,15 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     // coset iNTT with g^{-i} / Z(g) folded into the output table; result canonical = h
     if ((rc = ntt_run(ctx, pk->d_a, pk->d_a, pk->log_n, 1, nullptr, ct->inv_z.p, 0, 1, 0))) break;
     mark(E_NTT);
-    char* res = (char*)pk->d_results;
-    const char* z = (const char*)pk->d_z;
     {
-      // A, B1, L (G1) and B2 (G2) all take the witness as scalars: one digits + sort, four walks
-      const zkb_bases* qs[4] = {pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query};
-      void* outs4[4] = {res, res + 64, res + 256, res + 128};
+      // A, B1, L (G1) and B2 (G2) all take the witness as scalars: one digits + sort, four walks; the
+      // H walk follows and ONE tail reduces the four G1 bucket sets (msm_exec_prove)
+      const char* z = (const char*)pk->d_z;
       cudaEvent_t evs[4] = {ev[E_A], ev[E_B1], ev[E_L], ev[E_B2]};
-      if ((rc = msm_exec_multi(ctx, qs, 4, z + 32 * pk->qfirst[0], 0, pk->qcount[0], outs4, evs))) break;
+      if ((rc = msm_exec_prove(ctx, pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query, pk->h_query,
+                               z + 32 * pk->qfirst[0], pk->qcount[0], (const char*)pk->d_a + 32 * pk->qfirst[4],
+                               pk->qcount[4], pk->d_results, evs))) break;
     }
-    if ((rc = msm_exec(ctx, pk->h_query, 0, (const char*)pk->d_a + 32 * pk->qfirst[4], pk->qcount[4], res + 320))) break;
     mark(E_H);
     if (results_out_opt)
       cudaMemcpyAsync(results_out_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
@@ -820,15 +819,10 @@ static int prove_witness_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wi
 
 // the five MSMs over pk's ranges into pk->d_results (device, asynchronous); h from d_h (canonical,
 // pk's local h order)
-static int prove_msm_dev_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, cudaEvent_t ev_witness_msms = nullptr) {
-  char* res = (char*)pk->d_results;
+static int prove_msm_dev_phase(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h, cudaEvent_t* ev4_opt = nullptr) {
   const char* z = (const char*)pk->d_z;
-  const zkb_bases* qs[4] = {pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query};
-  void* outs4[4] = {res, res + 64, res + 256, res + 128};
-  int rc = msm_exec_multi(ctx, qs, 4, z + 32 * pk->qfirst[0], 0, pk->qcount[0], outs4, nullptr);
-  if (rc) return rc;
-  if (ev_witness_msms) cudaEventRecord(ev_witness_msms, ctx->stream);
-  return msm_exec(ctx, pk->h_query, 0, d_h, pk->qcount[4], res + 320);
+  return msm_exec_prove(ctx, pk->a_query, pk->b_g1_query, pk->l_query, pk->b_g2_query, pk->h_query,
+                        z + 32 * pk->qfirst[0], pk->qcount[0], d_h, pk->qcount[4], pk->d_results, ev4_opt);
 }
 
 // witness MSMs over pk's ranges + H MSM with h taken from d_h (canonical, pk's local h order)
@@ -915,11 +909,18 @@ int zkb_groth16_msm_dev(zkb_ctx* ctx, const zkb_pk* pk, const void* d_h,
   return prove_msm_only_phase(ctx, pk, d_h, partial_out);
 }
 
+// Layout of the evaluation vectors in the distributed witness map.  Every transform of the chain maps
+// layout d0 -> L - d0 -> d0 ..., i.e. it is one batch of size-2^d0 transforms plus one batch of
+// size-2^(L-d0) transforms.  d0 = 8 makes the first kind a SINGLE pass of the NTT kernel, so a
+// distributed transform costs as many passes as the single-GPU one (2^22: 1 + 2 instead of the
+// 2 + 2 of the balanced split 11 + 11); small circuits keep the balanced split.
+static uint32_t dist_low_bits(uint32_t log_n) { return log_n / 2 > 8 ? 8 : log_n / 2; }
+
 // ---- the whole proof over the ranks of ctx's communicator (collective; BASELINE.json configs[4])
 int zkb_pk_synthetic_dist(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out, uint8_t vk_out[ZKB_VK_BYTES]) {
   if (!ctx) return ZKB_EINVAL;
   if (!ctx->comm) return set_error(ctx, ZKB_EINVAL, "no communicator (zkb_comm_init first)");
-  const uint32_t world = uint32_t(ctx->comm->world), d0 = log_n / 2;
+  const uint32_t world = uint32_t(ctx->comm->world), d0 = dist_low_bits(log_n);
   if (log_n < 4 || ((1u << d0) % world))
     return set_error(ctx, ZKB_EINVAL, "circuit too small for this many ranks (need 2^(log_n/2) >= world)");
   return zkb_pk_synthetic_shard_ex(ctx, log_n, seed, uint32_t(ctx->comm->rank), world, log_n - d0, out, vk_out);
@@ -931,12 +932,12 @@ int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
   if (!witness || !r || !s || !proof_out) return set_error(ctx, ZKB_EINVAL, "null argument");
   Comm* cm = ctx->comm;
   if (!cm) return set_error(ctx, ZKB_EINVAL, "no communicator (zkb_comm_init first)");
-  const uint32_t L = pk->log_n, d0 = L / 2, d1 = L - d0, G = uint32_t(cm->world), g = uint32_t(cm->rank);
+  const uint32_t L = pk->log_n, d0 = dist_low_bits(L), d1 = L - d0, G = uint32_t(cm->world), g = uint32_t(cm->rank);
   if (pk->world != G || pk->rank != g || pk->h_low_bits != d1)
     return set_error(ctx, ZKB_EINVAL, "key was not built for this communicator (use zkb_pk_synthetic_dist)");
   const uint64_t n = pk->n, m = pk->m, n_loc = n / G;
   cudaStream_t st = ctx->stream;
-  enum { E_START, E_WIT, E_SPMV, E_NTT, E_MSMW, E_MSMH, E_END, E_COUNT };
+  enum { E_START, E_WIT, E_SPMV, E_NTT, E_A, E_B1, E_L, E_B2, E_MSMH, E_END, E_COUNT };
   cudaEvent_t ev[E_COUNT];
   for (int i = 0; i < E_COUNT; i++) ZKB_CUDA(ctx, cudaEventCreate(&ev[i]));
   int rc = ZKB_OK;
@@ -977,7 +978,7 @@ int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     fr_convert_launch(pk->d_a, n_loc, 0, st);
     cudaEventRecord(ev[E_NTT], st);
     // 4. the five MSMs over this rank's point ranges
-    if ((rc = prove_msm_dev_phase(ctx, pk, pk->d_a, ev[E_MSMW]))) break;
+    if ((rc = prove_msm_dev_phase(ctx, pk, pk->d_a, &ev[E_A]))) break;
     cudaEventRecord(ev[E_MSMH], st);
     // 5. 384 bytes per rank: all-gather, slot-wise sums, assemble — all on the device
     static const uint32_t offs[5] = {0, 64, 128, 256, 320}, g2s[5] = {0, 0, 1, 0, 0};
@@ -1006,8 +1007,11 @@ int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
       cudaEventElapsedTime(&timings_opt->ms_h2d, ev[E_START], ev[E_WIT]);
       cudaEventElapsedTime(&timings_opt->ms_spmv, ev[E_WIT], ev[E_SPMV]);
       cudaEventElapsedTime(&timings_opt->ms_ntt, ev[E_SPMV], ev[E_NTT]);
-      cudaEventElapsedTime(&timings_opt->ms_msm_a, ev[E_NTT], ev[E_MSMW]);     // A + B1 + L + B2 (one sort)
-      cudaEventElapsedTime(&timings_opt->ms_msm_h, ev[E_MSMW], ev[E_MSMH]);
+      cudaEventElapsedTime(&timings_opt->ms_msm_a, ev[E_NTT], ev[E_A]);        // shared sort + walk
+      cudaEventElapsedTime(&timings_opt->ms_msm_b1, ev[E_A], ev[E_B1]);
+      cudaEventElapsedTime(&timings_opt->ms_msm_l, ev[E_B1], ev[E_L]);
+      cudaEventElapsedTime(&timings_opt->ms_msm_b2, ev[E_L], ev[E_B2]);
+      cudaEventElapsedTime(&timings_opt->ms_msm_h, ev[E_B2], ev[E_MSMH]);      // sort + walk of H, then both tails
       cudaEventElapsedTime(&timings_opt->ms_total, ev[E_START], ev[E_END]);
     }
   } while (0);

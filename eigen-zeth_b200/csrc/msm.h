@@ -56,7 +56,7 @@ int msm_auto_window(uint64_t n, bool precomputed);
 // resident threads per SM the level-1 walk kernel of each curve is compiled for (launch bounds)
 uint32_t msm_l1_threads_per_sm_g1();
 uint32_t msm_l1_threads_per_sm_g2(int pair);
-// process-wide comparison switch (zkb_ctx_set "msm_g2_pair"): 1 = lane-pair G2 walk (default)
+// process-wide comparison switch (zkb_ctx_set "msm_g2_pair"): 1 = lane-pair G2 walk; default 0
 void msm_set_g2_pair(int on);
 int msm_get_g2_pair();
 // out[w * n + i] = 2^{c w} * in[i], w < nwin (affine Montgomery in and out; in may alias out[0..n))
@@ -74,6 +74,9 @@ void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
 void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
 void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);
+// ONE tail over p.n_sets (<= 8) bucket sets that belong to different MSMs (b.buckets = [set][half]);
+// set i writes its canonical affine result to d_outs[i]
+void msm_tail_multi_g1(const MsmPlan& p, const MsmBuffers& b, void* const* d_outs, uint32_t n, cudaStream_t s);
 // canonical affine -> Montgomery affine in place; every point that is neither the all-zero encoding
 // of infinity nor on the curve raises bit 1 of *d_flag (d_flag may be null: no check).
 // b_mont: the curve coefficient (8 / 16 Montgomery words, host pointer).

@@ -10,6 +10,12 @@ void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets
   msm_merge_t<Fq>(p, main_buckets, part_buckets, s);
 }
 void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) { msm_tail_t<Fq>(p, b, s); }
+void msm_tail_multi_g1(const MsmPlan& p, const MsmBuffers& b, void* const* d_outs, uint32_t n, cudaStream_t s) {
+  MsmOutPtrs o{};
+  o.n = n;
+  for (uint32_t i = 0; i < n && i < 8; i++) o.p[i] = d_outs[i];
+  msm_tail_t<Fq>(p, b, s, &o);
+}
 void msm_bases_to_mont_g1(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {
   msm_bases_to_mont_t<Fq>(d_pts, n, b_mont, d_flag, s);
 }

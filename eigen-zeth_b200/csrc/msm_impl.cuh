@@ -230,11 +230,19 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __re
 // per set: S + sum_l 16^l W_l (Horner over the reduce levels, 4 doublings each), then Horner over
 // the sets with c doublings each.  wl is [level][set]; s_tot is [set].
 // result (Montgomery XYZZ, 4*sizeof(F) bytes) and canonical affine (2*sizeof(F) bytes)
+// Independent mode (outs.n != 0): the sets are the bucket sets of DIFFERENT MSMs (one each, bases with
+// precomputed window multiples) reduced by one shared tail; set t writes its own canonical affine
+// result to outs.p[t] and nothing is combined across sets.
+struct MsmOutPtrs {
+  void* p[8];
+  uint32_t n;
+};
+
 template <class F>
 __global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ wl, const XYZZ<F>* __restrict__ s_tot,
                                   uint32_t levels, uint32_t n_sets, uint32_t c,
                                   XYZZ<F>* __restrict__ set_sums, XYZZ<F>* __restrict__ out_xyzz,
-                                  Affine<F>* __restrict__ out_affine) {
+                                  Affine<F>* __restrict__ out_affine, MsmOutPtrs outs) {
   const uint32_t t = threadIdx.x;
   if (blockIdx.x) return;
   if (t < n_sets) {
@@ -244,8 +252,16 @@ __global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ wl, const XYZZ<F>*
       acc.add(XYZZ<F>::load(wl + uint64_t(l) * n_sets + t));
     }
     acc.add(XYZZ<F>::load(s_tot + t));
-    acc.store(set_sums + t);
+    if (outs.n) {
+      Affine<F> a = acc.to_affine();
+      a.x = a.x.from_mont();
+      a.y = a.y.from_mont();
+      a.store(outs.p[t]);
+    } else {
+      acc.store(set_sums + t);
+    }
   }
+  if (outs.n) return;
   __syncthreads();
   if (t) return;
   XYZZ<F> acc = XYZZ<F>::load(set_sums + (n_sets - 1));
@@ -358,7 +374,7 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
 // scratch layout in b.group_sums (points): [runs of all levels][w0 of one level][stage 64*n_sets]
 // b.window_sums: [levels][n_sets] W_l, [n_sets] S, [n_sets] set sums
 template <class F>
-void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
+void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const MsmOutPtrs* independent = nullptr) {
   using P = XYZZ<F>;
   P* scratch = reinterpret_cast<P*>(b.group_sums);
   P* wl = reinterpret_cast<P*>(b.window_sums);
@@ -393,10 +409,12 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
     if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, s_tot);
     count_launches(slices > 1 ? 3 : 2);   // + the Horner kernel below
   }
+  MsmOutPtrs outs{};
+  if (independent) outs = *independent;
   msm_horner_kernel<F><<<1, 128, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,
                                          wl + uint64_t(p.red_levels + 1) * p.n_sets,
                                          reinterpret_cast<P*>(b.result_xyzz),
-                                         reinterpret_cast<Affine<F>*>(b.result_affine));
+                                         reinterpret_cast<Affine<F>*>(b.result_affine), outs);
   if (b.ev) cudaEventRecord(b.ev[5], s);
 }
 

@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
     r_base = (tile - blk * tiles_per_blk) << ct_bits;
     base = uint64_t(blk) * p.M + r_base;
     ncols = min(uint32_t(CT), p.S - r_base);
+  } else if (p.batch_cols) {
+    c_base = tile << ct_bits;               // first transform of this tile
+    ncols = min(uint32_t(CT), p.batch_count - c_base);
   } else {
     // a contiguous batch of transforms: tile -> (transform, tile within it)
     if (p.tiles_per_batch) {
@@ -166,10 +169,15 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
     uint32_t q = it * kThreads + tid;
     uint32_t c = q & (CT - 1);
     uint32_t t = q >> ct_bits;
+    if (FINAL && p.batch_cols && !p.in_ilv) {   // contiguous transforms: consecutive threads read one of them
+      t = q & ((1u << k) - 1);
+      c = q >> k;
+    }
     Fr x = Fr::zero();
     if (c < ncols) {
       uint64_t idx;
       if (!FINAL) idx = base + uint64_t(t) * p.S + c;
+      else if (p.batch_cols) idx = (uint64_t(c_base + c) << k) + t;
       else idx = batch_off + ((uint64_t(c_base + c) << mid_bits) + mid) * (1u << k) + t;
       uint64_t src = idx;
       if (p.in_ilv) src = ((idx & ((1ull << p.xform_log) - 1)) << p.in_ilv_log) + (idx >> p.xform_log);
@@ -262,6 +270,10 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
     uint32_t q = it * kThreads + tid;
     uint32_t c = q & (CT - 1);
     uint32_t K = q >> ct_bits;
+    if (FINAL && p.batch_cols) {        // consecutive threads walk one transform: contiguous 32 B * 2^k runs
+      K = q & ((1u << k) - 1);
+      c = q >> k;
+    }
     if (c >= ncols) continue;
     Fr y = sm_load(data, c >> gbits, ((c & ((1 << gbits) - 1)) << k) | K);
     uint64_t idx;
@@ -279,8 +291,12 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(NttPassArgs p) {
         y = y * w;
       }
     } else {
-      uint32_t rho = ((c_base + c) << mid_bits) + mid;
-      idx = batch_off + uint64_t(row_reverse(rho, p)) + (uint64_t(K) << p.row_bits);
+      if (p.batch_cols) {
+        idx = (uint64_t(c_base + c) << k) + K;
+      } else {
+        uint32_t rho = ((c_base + c) << mid_bits) + mid;
+        idx = batch_off + uint64_t(row_reverse(rho, p)) + (uint64_t(K) << p.row_bits);
+      }
       if (p.post_scale)
         y = y * Fr::load_nc(reinterpret_cast<const char*>(p.post_scale) + idx * 32);
     }

@@ -42,6 +42,11 @@ struct NttPassArgs {
   uint32_t out_col_bits;
   uint32_t xform_log;      // log2 of the transform size (splits a logical index into (b, i))
   void* out_wins[16];
+  // batch_cols (single-pass transforms only, P == 1): a tile's columns are CONSECUTIVE TRANSFORMS of a
+  // contiguous batch (8 << (8 - k) of them per CTA) instead of one transform per CTA with the other
+  // columns idle; logical index = transform * 2^k + element on both sides.
+  int batch_cols;
+  uint32_t batch_count;    // transforms in the batch (ragged last tile)
   uint32_t* flag;          // bit 0 raised when a canonical-form input (mont_in == 0) is >= r
   int mont_in;             // 0: input is canonical integers, convert while loading
   int mont_out;            // 0: convert the result back to canonical integers while storing

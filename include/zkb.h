@@ -55,8 +55,8 @@ void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
 /* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1),
  * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys),
- * "msm_g2_pair" (process-wide, default 1: the G2 bucket walk splits each Fq2 point operation over a
- * lane pair; 0 = the one-thread-per-point walk, kept for comparison) */
+ * "msm_g2_pair" (process-wide, default 0; 1 = the G2 bucket walk splits each Fq2 point operation
+ * over a lane pair — measured slower than one thread per point on B200, kept for comparison) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
 /* page-locked (pinned, portable) host memory for witnesses / scalars: H2D copies from it run at PCIe
@@ -224,6 +224,9 @@ uint32_t zkb_pk_log_n(const zkb_pk* pk);
 /* full witness assignment z (2^log_n canonical Fr, z[0] = 1, z[1] = public input) from two seeds */
 int zkb_synthetic_witness(uint32_t log_n, const uint8_t w0[32], const uint8_t w1[32],
                           uint8_t* z_out);
+/* device times: ms_msm_a = the witness digits + sort (shared by a, b_g1, l, b_g2) and the a_query
+ * walk; ms_msm_b1 / _l / _b2 = the bucket walks of those queries; ms_msm_h = sort + walk of the
+ * h_query MSM, then the bucket reductions (one shared by the four G1 MSMs, one for G2) */
 typedef struct zkb_prove_timings {
   float ms_h2d, ms_spmv, ms_ntt, ms_msm_a, ms_msm_b1, ms_msm_b2, ms_msm_l, ms_msm_h, ms_total;
 } zkb_prove_timings;
@@ -259,8 +262,7 @@ int zkb_groth16_assemble(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t sums[ZKB_
  * passes the same full witness (host pointer: each uploads 1/world of it over PCIe and the slices
  * are all-gathered over NVLink; or a device pointer) and every rank receives the proof.  Witness
  * map: 7 four-step NTTs; MSMs: sharded by point range; the 384-byte partial sums are gathered,
- * added and assembled on the device.  timings: ms_h2d = witness staging, ms_spmv, ms_ntt,
- * ms_msm_a = the four witness MSMs (one shared sort), ms_msm_h, ms_total. */
+ * added and assembled on the device.  timings as for zkb_groth16_prove (ms_h2d = witness staging). */
 int zkb_pk_synthetic_dist(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** out,
                           uint8_t vk_out[ZKB_VK_BYTES]);
 int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],

@@ -39,6 +39,7 @@ for pair in (0, 1, 0, 1):
     res[key]["msm_ms"].append(statistics.median(ts))
     res[key]["walk_ms"].append(statistics.median(l1))
     res[key]["result"] = bytes(out.cpu().numpy()).hex()
+    res[key]["stage_ms"] = {k: round(v, 3) for k, v in ctx.msm_last_timings().items()}
 c = bases.window
 nwin = (255 + c - 1) // c
 imads = n * nwin * (8 * 400 + 2 * 272)          # 8 Fq2 products + 2 Fq2 squarings per mixed addition
