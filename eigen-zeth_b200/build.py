@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
                   "--expt-relaxed-constexpr"]
-CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden"]
+CXXFLAGS = ["-O3", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-fvisibility=hidden"]
 
 
 def _sources():
@@ -47,9 +47,14 @@ def _deps_mtime(path, seen=None):
     return m
 
 
+# per-file defines: the G2 MSM translation unit calls ONE out-of-line Fq2 product / square instead of
+# inlining ten of them per mixed addition (instruction-cache footprint of the bucket walk, ff.cuh)
+PER_FILE = {"msm_g2.cu": ["-DZKB_FQ2_CALLS"]}
+
+
 def _compile(src, obj):
     if src.endswith(".cu"):
-        cmd = [NVCC] + CUFLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + CUFLAGS + PER_FILE.get(os.path.basename(src), []) + ["-c", src, "-o", obj]
     else:
         cmd = ["g++"] + CXXFLAGS + ["-I/usr/local/cuda/include", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)

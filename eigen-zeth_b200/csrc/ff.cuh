@@ -628,16 +628,35 @@ struct Fq2 {
   }
   // Two fused dual products (a0 b0 - a1 b1, a0 b1 + a1 b0): 2 x 200 IMAD.WIDE, against 3 x 136 for
   // Karatsuba — and without Karatsuba's five 256-bit additions / subtractions and their temporaries.
-  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) {
+  __device__ __forceinline__ static Fq2 mul_inline(const Fq2& a, const Fq2& b) {
     return {Fq::mul_sub_mul(a.c0, b.c0, a.c1, b.c1), Fq::mul_add_mul(a.c0, b.c1, a.c1, b.c0)};
   }
+#ifdef ZKB_FQ2_CALLS
+  // The G2 bucket walk inlines ten Fq2 products per mixed addition: ~10 k instructions = 158 KB of
+  // straight-line code per loop turn, far beyond the instruction cache — ncu shows warps stalled on
+  // instruction fetch (`stalled_no_instruction` 0.63 per issue, against 0.06 in the G1 walk whose
+  // loop is 54 KB).  Compiled as ONE out-of-line routine (operands and result in registers, no
+  // stack), the loop body shrinks to a few KB.
+  __device__ __noinline__ static Fq2 mul_call(Fq2 a, Fq2 b) { return mul_inline(a, b); }
+  __device__ __noinline__ static Fq2 sqr_call(Fq2 a) {
+    Fq t = a.c0 * a.c1;
+    return {(a.c0 + a.c1) * (a.c0 - a.c1), t.dbl()};
+  }
+  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) { return mul_call(a, b); }
+#else
+  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) { return mul_inline(a, b); }
+#endif
   __device__ __forceinline__ static Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
     return a * b - c * d;
   }
   // (a0+a1)(a0-a1), 2 a0 a1 : 2 Fq multiplications
   __device__ __forceinline__ Fq2 sqr() const {
+#ifdef ZKB_FQ2_CALLS
+    return sqr_call(*this);
+#else
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
+#endif
   }
   __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   __device__ __forceinline__ Fq2 neg() const { return {c0.neg(), c1.neg()}; }

@@ -19,6 +19,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "ff.cuh"
 #include "ntt.h"
@@ -382,14 +383,17 @@ __global__ void fr_mul_sub_kernel(Fr* a, const Fr* b, const Fr* c, uint64_t n) {
 
 // ---------------------------------------------------------------- host side
 void ntt_launch_pass(const NttPassArgs& a, bool final, uint32_t tiles, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to 64 KB of dynamic shared memory is per device: once for every GPU this process uses
+  // (several contexts / host threads may launch concurrently)
+  static std::once_flag configured[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(configured[dev & 63], [] {
     cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(kSmemBytes));
     cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(kSmemBytes));
-    configured = true;
-  }
+  });
   if (final)
     ntt_pass_kernel<true><<<tiles, kThreads, kSmemBytes, s>>>(a);
   else

@@ -10,6 +10,7 @@
 // D-type twist E': y^2 = x^3 + 3/xi, untwist (x, y) -> (x w^2, y w^3).
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/zkb.h"
 #include "host_ff.hpp"
@@ -142,13 +143,51 @@ G1 g1_add(const G1& p, const G1& q) {
   HFq x3 = lam.sqr() - p.x - q.x;
   return {x3, lam * (p.x - x3) - p.y, false};
 }
+// k * P in Jacobian coordinates (one inversion at the end instead of one per ladder step)
 G1 g1_mul(const G1& p, const uint64_t k[4]) {
-  G1 r{HFq::zero(), HFq::zero(), true};
+  if (p.inf) return p;
+  HFq X = HFq::one(), Y = HFq::one(), Z = HFq::zero();      // infinity
   for (int i = 255; i >= 0; i--) {
-    r = g1_add(r, r);
-    if ((k[i >> 6] >> (i & 63)) & 1) r = g1_add(r, p);
+    if (!Z.is_zero()) {                                      // dbl-2009-l (a = 0)
+      HFq a = X.sqr(), b = Y.sqr(), c = b.sqr();
+      HFq d = (X + b).sqr() - a - c;
+      d = d + d;
+      HFq e = a + a + a, f = e.sqr();
+      HFq x3 = f - d - d;
+      HFq c8 = c + c;
+      c8 = c8 + c8;
+      c8 = c8 + c8;
+      HFq z3 = Y * Z;
+      Y = e * (d - x3) - c8;
+      X = x3;
+      Z = z3 + z3;
+    }
+    if ((k[i >> 6] >> (i & 63)) & 1) {
+      if (Z.is_zero()) {
+        X = p.x; Y = p.y; Z = HFq::one();
+      } else {                                               // madd: affine p
+        HFq z2 = Z.sqr();
+        HFq u2 = p.x * z2, s2 = p.y * z2 * Z;
+        HFq h = u2 - X, rr = s2 - Y;
+        if (h.is_zero()) {
+          if (!rr.is_zero()) { Z = HFq::zero(); continue; }  // P + (-P)
+          // P + P: fall back to the affine doubling of p (cannot happen for k < r with P of order r,
+          // kept for completeness)
+          G1 d2 = g1_add(p, p);
+          X = d2.x; Y = d2.y; Z = d2.inf ? HFq::zero() : HFq::one();
+          continue;
+        }
+        HFq h2 = h.sqr(), h3 = h2 * h, v = X * h2;
+        HFq x3 = rr.sqr() - h3 - v - v;
+        Y = rr * (v - x3) - Y * h3;
+        X = x3;
+        Z = Z * h;
+      }
+    }
   }
-  return r;
+  if (Z.is_zero()) return {HFq::zero(), HFq::zero(), true};
+  HFq zi = Z.inverse(), zi2 = zi.sqr();
+  return {X * zi2, Y * zi2 * zi, false};
 }
 G2 g2_add(const G2& p, const G2& q) {
   if (p.inf) return q;
@@ -164,34 +203,96 @@ G2 g2_add(const G2& p, const G2& q) {
   F2 x3 = lam.sqr() - p.x - q.x;
   return {x3, lam * (p.x - x3) - p.y, false};
 }
-// r * P == O  (subgroup membership on the twist; G1 has cofactor 1)
+// r * P == O  (subgroup membership on the twist; G1 has cofactor 1).  Jacobian coordinates: no field
+// inversion inside the 254-step ladder (the affine ladder spent ~400 Fq multiplications per step on it).
+struct G2J {
+  F2 x, y, z;   // affine (x / z^2, y / z^3); z == 0: infinity
+};
+G2J g2j_dbl(const G2J& p) {
+  if (p.z.is_zero()) return p;
+  F2 a = p.x.sqr(), b = p.y.sqr(), c = b.sqr();
+  F2 d = (p.x + b).sqr() - a - c;
+  d = d + d;
+  F2 e = a + a + a, f = e.sqr();
+  F2 x3 = f - d - d;
+  F2 c8 = c + c;
+  c8 = c8 + c8;
+  c8 = c8 + c8;
+  F2 y3 = e * (d - x3) - c8;
+  F2 z3 = p.y * p.z;
+  return {x3, y3, z3 + z3};
+}
+G2J g2j_add_affine(const G2J& p, const G2& q) {     // q affine, not infinity
+  if (p.z.is_zero()) return {q.x, q.y, F2::one()};
+  F2 z2 = p.z.sqr();
+  F2 u2 = q.x * z2, s2 = q.y * z2 * p.z;
+  F2 h = u2 - p.x, rr = s2 - p.y;
+  if (h.is_zero()) {
+    if (rr.is_zero()) return g2j_dbl(p);
+    return {F2::one(), F2::one(), F2::zero()};
+  }
+  F2 h2 = h.sqr(), h3 = h2 * h, v = p.x * h2;
+  F2 x3 = rr.sqr() - h3 - v - v;
+  F2 y3 = rr * (v - x3) - p.y * h3;
+  return {x3, y3, p.z * h};
+}
 bool g2_in_subgroup(const G2& p) {
   if (p.inf) return true;
-  G2 r{F2::zero(), F2::zero(), true};
+  G2J r{F2::one(), F2::one(), F2::zero()};
   for (int i = 255; i >= 0; i--) {
-    r = g2_add(r, r);
-    if ((zkb::host::FrCfg::MOD[i >> 6] >> (i & 63)) & 1) r = g2_add(r, p);
+    r = g2j_dbl(r);
+    if ((zkb::host::FrCfg::MOD[i >> 6] >> (i & 63)) & 1) r = g2j_add_affine(r, p);
   }
-  return r.inf;
+  return r.z.is_zero();
 }
 
-// line through T and S (tangent if equal) on the twist, evaluated at P; T <- T + S.
-// l = yP - lam xP w + (lam xT - yT) w^3, w^3 = v w  ->  c0 = (yP,0,0), c1 = (-lam xP, lam xT - yT, 0)
-F12 line(G2& T, const G2& S, const G1& P) {
-  F2 lam;
-  if (T.x == S.x && T.y == S.y) {
-    F2 xx = T.x.sqr();
-    lam = (xx + xx + xx) * (T.y + T.y).inverse();
-  } else {
-    lam = (S.y - T.y) * (S.x - T.x).inverse();
+// Lines of the optimal-ate Miller loop, for up to four pairs at once.  Step j of pair k needs the
+// slope lam = num / den on the twist (tangent: 3 x^2 / 2 y, chord: (yS - yT) / (xS - xT)); the
+// denominators of all pairs are inverted together (Montgomery's trick on the Fq norms: ONE field
+// inversion per step instead of one per pair), then each pair finishes its line
+//   l = yP - lam xP w + (lam xT - yT) w^3,  w^3 = v w  ->  c0 = (yP,0,0), c1 = (-lam xP, lam xT - yT, 0)
+// and moves T <- T + S.
+constexpr int kMaxPairs = 4;
+void batch_inverse_f2(F2* v, int n) {          // v[i] <- 1 / v[i]; all non-zero
+  HFq norm[kMaxPairs], pre[kMaxPairs];
+  HFq acc = HFq::one();
+  for (int i = 0; i < n; i++) {
+    norm[i] = v[i].a.sqr() + v[i].b.sqr();
+    pre[i] = acc;
+    acc = acc * norm[i];
   }
-  F2 x3 = lam.sqr() - T.x - S.x;
-  F2 y3 = lam * (T.x - x3) - T.y;
-  F12 l;
-  l.c0 = {F2{P.y, HFq::zero()}, F2::zero(), F2::zero()};
-  l.c1 = {lam.scale(P.x).neg(), lam * T.x - T.y, F2::zero()};
-  T = {x3, y3, false};
-  return l;
+  HFq inv = acc.inverse();
+  for (int i = n - 1; i >= 0; i--) {
+    HFq ni = inv * pre[i];
+    inv = inv * norm[i];
+    v[i] = {v[i].a * ni, (v[i].b * ni).neg()};
+  }
+}
+// one step for every pair: T[k] <- T[k] + S[k] (S == nullptr: doubling); f <- f * prod_k line_k
+void line_step(F12& f, G2* T, const G2* S, const G1* P, int n) {
+  F2 num[kMaxPairs], den[kMaxPairs];
+  for (int k = 0; k < n; k++) {
+    if (!S || (T[k].x == S[k].x && T[k].y == S[k].y)) {
+      F2 xx = T[k].x.sqr();
+      num[k] = xx + xx + xx;
+      den[k] = T[k].y + T[k].y;
+    } else {
+      num[k] = S[k].y - T[k].y;
+      den[k] = S[k].x - T[k].x;
+    }
+  }
+  batch_inverse_f2(den, n);
+  for (int k = 0; k < n; k++) {
+    const G2& Sk = S ? S[k] : T[k];
+    F2 lam = num[k] * den[k];
+    F2 x3 = lam.sqr() - T[k].x - Sk.x;
+    F2 y3 = lam * (T[k].x - x3) - T[k].y;
+    F12 l;
+    l.c0 = {F2{P[k].y, HFq::zero()}, F2::zero(), F2::zero()};
+    l.c1 = {lam.scale(P[k].x).neg(), lam * T[k].x - T[k].y, F2::zero()};
+    T[k] = {x3, y3, false};
+    f = f * l;
+  }
 }
 
 struct Frob {
@@ -217,19 +318,25 @@ G2 frobenius(const G2& p, const Frob& f) { return {p.x.conj() * f.gx, p.y.conj()
 
 const uint64_t ATE_LOOP[2] = {0x9d797039be763ba8ull, 0x1ull};   // 6x + 2 = 29793968203157093288
 
-F12 miller(const G1& P, const G2& Q, const Frob& fr) {
-  if (P.inf || Q.inf) return F12::one();
+// prod_k f_{6x+2, Q_k}(P_k) with ONE shared accumulator: one F12 squaring per loop step whatever the
+// number of pairs.  Pairs with a point at infinity contribute 1 and are dropped by the caller.
+F12 multi_miller(const G1* P, const G2* Q, int n, const Frob& fr) {
   F12 f = F12::one();
-  G2 T = Q;
+  if (n == 0) return f;
+  G2 T[kMaxPairs], Q1[kMaxPairs], Q2[kMaxPairs];
+  for (int k = 0; k < n; k++) T[k] = Q[k];
   for (int i = 63; i >= 0; i--) {   // bit 64 is the leading one
-    f = f.sqr() * line(T, T, P);
-    if ((ATE_LOOP[0] >> i) & 1) f = f * line(T, Q, P);
+    f = f.sqr();
+    line_step(f, T, nullptr, P, n);
+    if ((ATE_LOOP[0] >> i) & 1) line_step(f, T, Q, P, n);
   }
-  G2 Q1 = frobenius(Q, fr);
-  G2 Q2 = frobenius(Q1, fr);
-  Q2.y = Q2.y.neg();
-  f = f * line(T, Q1, P);
-  f = f * line(T, Q2, P);
+  for (int k = 0; k < n; k++) {
+    Q1[k] = frobenius(Q[k], fr);
+    Q2[k] = frobenius(Q1[k], fr);
+    Q2[k].y = Q2[k].y.neg();
+  }
+  line_step(f, T, Q1, P, n);
+  line_step(f, T, Q2, P, n);
   return f;
 }
 
@@ -255,10 +362,75 @@ F12 f12_pow(const F12& b, const uint64_t* e, int words) {
   }
   return r;
 }
-F12 final_exp(const F12& f) {
+// reference form: plain square-and-multiply on both exponents (kept as the checker of the fast one)
+F12 final_exp_slow(const F12& f) {
   F12 t = f.conj() * f.inverse();     // f^{q^6 - 1}
   t = f12_pow(t, Q2P1, 8);            // ^(q^2 + 1)
   return f12_pow(t, HARD, 12);        // ^((q^4 - q^2 + 1)/r)
+}
+
+// Frobenius on Fq12 = Fq2[w]/(w^6 - xi): (sum c_i w^i)^(q^k) = sum conj^k(c_i) g_{k,i} w^i with
+// g_{k,i} = xi^(i (q^k - 1)/6).  In the tower basis w^0..w^5 = c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2.
+struct Frob12 {
+  F2 g[4][6];     // g[k][i], k = 1, 2, 3
+  Frob12() {
+    F2 xi{HFq::from_u64(9), HFq::one()};
+    uint64_t q1[4] = {zkb::host::FqCfg::MOD[0] - 1, zkb::host::FqCfg::MOD[1], zkb::host::FqCfg::MOD[2],
+                      zkb::host::FqCfg::MOD[3]};
+    uint64_t e6[4];
+    unsigned __int128 rem = 0;
+    for (int i = 3; i >= 0; i--) {
+      unsigned __int128 cur = (rem << 64) | q1[i];
+      e6[i] = (uint64_t)(cur / 6);
+      rem = cur % 6;
+    }
+    F2 g1 = f2_pow(xi, e6, 4);        // xi^((q-1)/6)
+    F2 p = F2::one();
+    for (int i = 0; i < 6; i++) {
+      g[1][i] = p;
+      g[2][i] = p * p.conj();         // ^(q+1): the norm, in Fq
+      g[3][i] = g[2][i] * p;          // ^(q^2+q+1)
+      p = p * g1;
+    }
+  }
+  F12 apply(const F12& f, int k) const {
+    const F2* c[6] = {&f.c0.c0, &f.c1.c0, &f.c0.c1, &f.c1.c1, &f.c0.c2, &f.c1.c2};
+    F2 r[6];
+    for (int i = 0; i < 6; i++) r[i] = ((k & 1) ? c[i]->conj() : *c[i]) * g[k][i];
+    return {{r[0], r[2], r[4]}, {r[1], r[3], r[5]}};
+  }
+};
+
+F12 f12_pow_x(const F12& b) {         // ^x, x = 4965661367192848881 (the BN parameter)
+  static const uint64_t X[1] = {4965661367192848881ull};
+  return f12_pow(b, X, 1);
+}
+
+// f^{(q^12-1)/r}: easy part with one inversion and one Frobenius; hard part (q^4 - q^2 + 1)/r by the
+// Devegili / Scott decomposition in base q with three powers by x (63 bits each) — ~260 Fq12
+// operations instead of ~1900 for plain square-and-multiply.  In the cyclotomic subgroup the
+// inverse is the conjugate.  tests/test_abi_host.py compares it with final_exp_slow on pairing values.
+F12 final_exp(const F12& f) {
+  static const Frob12 fb;
+  F12 t1 = f.conj() * f.inverse();                  // f^(q^6 - 1)
+  t1 = fb.apply(t1, 2) * t1;                        // ^(q^2 + 1)
+  F12 fp = fb.apply(t1, 1), fp2 = fb.apply(t1, 2), fp3 = fb.apply(fp2, 1);
+  F12 fu = f12_pow_x(t1), fu2 = f12_pow_x(fu), fu3 = f12_pow_x(fu2);
+  F12 y3 = fb.apply(fu, 1).conj();
+  F12 fu2p = fb.apply(fu2, 1), fu3p = fb.apply(fu3, 1);
+  F12 y2 = fb.apply(fu2, 2);
+  F12 y0 = fp * fp2 * fp3;
+  F12 y1 = t1.conj();
+  F12 y5 = fu2.conj();
+  F12 y4 = (fu * fu2p).conj();
+  F12 y6 = (fu3 * fu3p).conj();
+  F12 t0 = y6.sqr() * y4 * y5;
+  F12 s1 = y3 * y5 * t0;
+  t0 = t0 * y2;
+  s1 = (s1.sqr() * t0).sqr();
+  t0 = s1 * y1;
+  s1 = s1 * y0;
+  return t0.sqr() * s1;
 }
 
 bool read_fq(const uint8_t* b, HFq* out) { return HFq::from_bytes(b, out); }
@@ -291,9 +463,26 @@ extern "C" int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t 
   if (!vk || !proof || !public_input) return ZKB_EINVAL;
   G1 alpha, ic0, ic1, A, C;
   G2 beta, gamma, delta, B;
-  if (!read_g1(vk, &alpha) || !read_g2(vk + 64, &beta) || !read_g2(vk + 192, &gamma) ||
-      !read_g2(vk + 320, &delta) || !read_g1(vk + 448, &ic0) || !read_g1(vk + 512, &ic1))
-    return ZKB_EINVAL;
+  // a verifier checks many proofs against one key: the key's own validation (on-curve, three G2
+  // subgroup checks) is remembered for the last key seen
+  {
+    static std::mutex mu;
+    static uint8_t last_vk[ZKB_VK_BYTES];
+    static bool have = false;
+    static G1 c_alpha, c_ic0, c_ic1;
+    static G2 c_beta, c_gamma, c_delta;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have || std::memcmp(last_vk, vk, ZKB_VK_BYTES) != 0) {
+      have = false;
+      if (!read_g1(vk, &c_alpha) || !read_g2(vk + 64, &c_beta) || !read_g2(vk + 192, &c_gamma) ||
+          !read_g2(vk + 320, &c_delta) || !read_g1(vk + 448, &c_ic0) || !read_g1(vk + 512, &c_ic1))
+        return ZKB_EINVAL;
+      std::memcpy(last_vk, vk, ZKB_VK_BYTES);
+      have = true;
+    }
+    alpha = c_alpha; ic0 = c_ic0; ic1 = c_ic1;
+    beta = c_beta; gamma = c_gamma; delta = c_delta;
+  }
   if (!read_g1(proof, &A) || !read_g2(proof + 64, &B) || !read_g1(proof + 192, &C)) return ZKB_EINVAL;
   uint64_t x[4];
   std::memcpy(x, public_input, 32);
@@ -301,9 +490,35 @@ extern "C" int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t 
   G1 acc = g1_add(ic0, g1_mul(ic1, x));
   static const Frob fr;
   auto negp = [](G1 p) { p.y = p.y.neg(); return p; };
-  F12 f = miller(A, B, fr) * miller(negp(alpha), beta, fr) * miller(negp(acc), gamma, fr) *
-          miller(negp(C), delta, fr);
-  return final_exp(f) == F12::one() ? ZKB_OK : ZKB_EVERIFY;
+  // e(A,B) e(-alpha,beta) e(-acc,gamma) e(-C,delta) == 1: one shared Miller loop, one final exponentiation
+  const G1 Ps[4] = {A, negp(alpha), negp(acc), negp(C)};
+  const G2 Qs[4] = {B, beta, gamma, delta};
+  G1 P[4];
+  G2 Q[4];
+  int n = 0;
+  for (int k = 0; k < 4; k++)
+    if (!Ps[k].inf && !Qs[k].inf) {
+      P[n] = Ps[k];
+      Q[n++] = Qs[k];
+    }
+  return final_exp(multi_miller(P, Q, n, fr)) == F12::one() ? ZKB_OK : ZKB_EVERIFY;
+}
+
+// test hook (tests/test_abi_host.py): 0 when the decomposed final exponentiation agrees with plain
+// square-and-multiply on e(k1 G1, G2-point)-style Miller values built from the given proof points
+extern "C" int zkb_selftest_final_exp(const uint8_t proof[ZKB_PROOF_BYTES]) {
+  G1 A, C;
+  G2 B;
+  if (!proof || !read_g1(proof, &A) || !read_g2(proof + 64, &B) || !read_g1(proof + 192, &C)) return ZKB_EINVAL;
+  if (A.inf || B.inf || C.inf) return ZKB_EINVAL;
+  static const Frob fr;
+  const G1 P[2] = {A, C};
+  const G2 Q[2] = {B, B};
+  for (int n = 1; n <= 2; n++) {
+    F12 m = multi_miller(P, Q, n, fr);
+    if (!(final_exp(m) == final_exp_slow(m))) return ZKB_EVERIFY;
+  }
+  return ZKB_OK;
 }
 
 extern "C" int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_input[32],

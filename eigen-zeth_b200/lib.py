@@ -31,7 +31,7 @@ EXPORTS = [
     "zkb_comm_unique_id", "zkb_comm_init", "zkb_comm_init_local", "zkb_comm_rank", "zkb_comm_world",
     "zkb_comm_transport", "zkb_comm_barrier", "zkb_comm_destroy", "zkb_fr_ntt_dist_dev",
     "zkb_fr_index_power_table_dist", "zkb_msm_g1_dist_dev", "zkb_msm_g2_dist_dev", "zkb_msm_g1_dist",
-    "zkb_msm_g2_dist", "zkb_pk_synthetic_dist", "zkb_groth16_prove_dist",
+    "zkb_msm_g2_dist", "zkb_pk_synthetic_dist", "zkb_groth16_prove_dist", "zkb_selftest_final_exp",
 ]
 COMM_ID_BYTES = 128
 
@@ -134,6 +134,7 @@ def load_library() -> C.CDLL:
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
         lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
+        lib.zkb_selftest_final_exp.argtypes = [u8p]
     lib.zkb_comm_unique_id.argtypes = [vp]
     lib.zkb_comm_init.argtypes = [vp, u8p, i32, i32]
     lib.zkb_comm_init_local.argtypes = [C.POINTER(vp), i32]

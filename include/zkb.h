@@ -289,6 +289,10 @@ int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_P
 int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_input[32],
                     uint32_t* reasons_opt);
 
+/* test hook: the decomposed final exponentiation of the verifier against plain square-and-multiply on
+ * Miller values built from the proof's points; ZKB_OK when they agree */
+int zkb_selftest_final_exp(const uint8_t proof[ZKB_PROOF_BYTES]);
+
 /* ---- circuit files -------------------------------------------------------------
  * Readers for the iden3 binary formats circom / snarkjs write (.r1cs constraint systems, .wtns
  * witnesses) over BN254's scalar field; host code, no allocation.  Wire order is

@@ -292,3 +292,26 @@ def test_python_binding_checks_buffer_lengths(zkb):
         pk.witness_ptr(bytes(32 * 15))
     ptr, keep = pk.witness_ptr(bytes(32 * 16))
     assert ptr.value and keep is not None
+
+
+def test_fast_final_exponentiation_equals_square_and_multiply(zkb):
+    """the verifier's hard part uses the base-q decomposition with three powers by the BN parameter and
+    Frobenius maps; it must give exactly what plain square-and-multiply on (q^12 - 1) / r gives"""
+    log_n, seed = 5, 31
+    opk = ob.ProvingKey(log_n, seed)
+    wit = ob.synthetic_witness(log_n, fr_bytes([3]), fr_bytes([4]))
+    proof, _, _, _ = opk.prove(wit, fr_bytes([5]), fr_bytes([6]))
+    assert zkb.load_library().zkb_selftest_final_exp(proof) == 0
+    assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])
+    assert not zkb.groth16_verify(opk.vk(), proof, wit[64:96])
+    # same key again (memoised key validation), another key (memo replaced), the first key again
+    opk2 = ob.ProvingKey(log_n, seed + 1)
+    proof2, _, _, _ = opk2.prove(wit, fr_bytes([5]), fr_bytes([6]))
+    assert zkb.groth16_verify(opk2.vk(), proof2, wit[32:64])
+    assert not zkb.groth16_verify(opk2.vk(), proof, wit[32:64])
+    assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])
+    bad_vk = bytearray(opk.vk())
+    bad_vk[64] ^= 1                                        # beta_g2 leaves the twist
+    with pytest.raises(zkb.ZkbError):
+        zkb.groth16_verify(bytes(bad_vk), proof, wit[32:64])
+    assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])

@@ -40,6 +40,7 @@ def _assemble(group, blocks, log_n, d):
     for g, blk in enumerate(blocks):
         full[:, g] = blk.view(lows, highs, 32).permute(1, 0, 2)
     full = full.view(-1).contiguous()
+    torch.cuda.synchronize()          # the library streams are non-blocking: they do not wait for torch's copies
     group.ctxs[0].fr_convert_dev(full.data_ptr(), 1 << log_n, False)
     group.ctxs[0].sync()
     return bytes(full.cpu().numpy())
