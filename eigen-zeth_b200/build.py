@@ -47,9 +47,7 @@ def _deps_mtime(path, seen=None):
     return m
 
 
-# per-file defines: the G2 MSM translation unit calls ONE out-of-line Fq2 product / square instead of
-# inlining ten of them per mixed addition (instruction-cache footprint of the bucket walk, ff.cuh)
-PER_FILE = {"msm_g2.cu": ["-DZKB_FQ2_CALLS"]}
+PER_FILE = {}     # per-file extra flags (none at present)
 
 
 def _compile(src, obj):

@@ -601,17 +601,25 @@ using Fq = Fp<FqParams>;
 using Fr = Fp<FrParams>;
 
 // ---------------------------------------------------------------- Fq2 = Fq[u]/(u^2+1)
-struct Fq2 {
+// CALLS = false: every product is inlined (the bucket walk: straight-line code, best pipe use).
+// CALLS = true: products and squares are ONE out-of-line routine each (operands and result in
+// registers, no stack).  The latency-bound G2 kernels around the walk (partial merges, bucket
+// reduction, window sums, Horner) inline 15-60 products per loop turn otherwise — hundreds of KB of
+// straight-line code whose instruction-cache misses showed up as `stalled_no_instruction` in ncu;
+// with the call form the G2 bucket-reduction tail went from 2.16 to 1.73 ms (2^19 points), while the
+// walk itself is 3 % FASTER inlined (the call moves cost more than the cache misses), so it stays so.
+template <bool CALLS>
+struct Fq2T {
   Fq c0, c1;
   static constexpr int kBytes = 64;
   static constexpr int kLanes = 1;
-  __device__ __forceinline__ static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
-  __device__ __forceinline__ static Fq2 one() { return {Fq::one(), Fq::zero()}; }
-  __device__ __forceinline__ static Fq2 load(const void* p) {
+  __device__ __forceinline__ static Fq2T zero() { return {Fq::zero(), Fq::zero()}; }
+  __device__ __forceinline__ static Fq2T one() { return {Fq::one(), Fq::zero()}; }
+  __device__ __forceinline__ static Fq2T load(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
     return {Fq::load(c), Fq::load(c + 32)};
   }
-  __device__ __forceinline__ static Fq2 load_nc(const void* p) {
+  __device__ __forceinline__ static Fq2T load_nc(const void* p) {
     const char* c = reinterpret_cast<const char*>(p);
     return {Fq::load_nc(c), Fq::load_nc(c + 32)};
   }
@@ -620,61 +628,54 @@ struct Fq2 {
     c0.store(c);
     c1.store(c + 32);
   }
-  __device__ __forceinline__ friend Fq2 operator+(const Fq2& a, const Fq2& b) {
+  __device__ __forceinline__ friend Fq2T operator+(const Fq2T& a, const Fq2T& b) {
     return {a.c0 + b.c0, a.c1 + b.c1};
   }
-  __device__ __forceinline__ friend Fq2 operator-(const Fq2& a, const Fq2& b) {
+  __device__ __forceinline__ friend Fq2T operator-(const Fq2T& a, const Fq2T& b) {
     return {a.c0 - b.c0, a.c1 - b.c1};
   }
   // Two fused dual products (a0 b0 - a1 b1, a0 b1 + a1 b0): 2 x 200 IMAD.WIDE, against 3 x 136 for
   // Karatsuba — and without Karatsuba's five 256-bit additions / subtractions and their temporaries.
-  __device__ __forceinline__ static Fq2 mul_inline(const Fq2& a, const Fq2& b) {
+  __device__ __forceinline__ static Fq2T mul_inline(const Fq2T& a, const Fq2T& b) {
     return {Fq::mul_sub_mul(a.c0, b.c0, a.c1, b.c1), Fq::mul_add_mul(a.c0, b.c1, a.c1, b.c0)};
   }
-#ifdef ZKB_FQ2_CALLS
-  // The G2 bucket walk inlines ten Fq2 products per mixed addition: ~10 k instructions = 158 KB of
-  // straight-line code per loop turn, far beyond the instruction cache — ncu shows warps stalled on
-  // instruction fetch (`stalled_no_instruction` 0.63 per issue, against 0.06 in the G1 walk whose
-  // loop is 54 KB).  Compiled as ONE out-of-line routine (operands and result in registers, no
-  // stack), the loop body shrinks to a few KB.
-  __device__ __noinline__ static Fq2 mul_call(Fq2 a, Fq2 b) { return mul_inline(a, b); }
-  __device__ __noinline__ static Fq2 sqr_call(Fq2 a) {
+  // (a0+a1)(a0-a1), 2 a0 a1 : 2 Fq multiplications
+  __device__ __forceinline__ static Fq2T sqr_inline(const Fq2T& a) {
     Fq t = a.c0 * a.c1;
     return {(a.c0 + a.c1) * (a.c0 - a.c1), t.dbl()};
   }
-  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) { return mul_call(a, b); }
-#else
-  __device__ __forceinline__ friend Fq2 operator*(const Fq2& a, const Fq2& b) { return mul_inline(a, b); }
-#endif
-  __device__ __forceinline__ static Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+  __device__ __noinline__ static Fq2T mul_call(Fq2T a, Fq2T b) { return mul_inline(a, b); }
+  __device__ __noinline__ static Fq2T sqr_call(Fq2T a) { return sqr_inline(a); }
+  __device__ __forceinline__ friend Fq2T operator*(const Fq2T& a, const Fq2T& b) {
+    if constexpr (CALLS) return mul_call(a, b);
+    else return mul_inline(a, b);
+  }
+  __device__ __forceinline__ static Fq2T mul_sub_mul(const Fq2T& a, const Fq2T& b, const Fq2T& c, const Fq2T& d) {
     return a * b - c * d;
   }
-  // (a0+a1)(a0-a1), 2 a0 a1 : 2 Fq multiplications
-  __device__ __forceinline__ Fq2 sqr() const {
-#ifdef ZKB_FQ2_CALLS
-    return sqr_call(*this);
-#else
-    Fq t = c0 * c1;
-    return {(c0 + c1) * (c0 - c1), t.dbl()};
-#endif
+  __device__ __forceinline__ Fq2T sqr() const {
+    if constexpr (CALLS) return sqr_call(*this);
+    else return sqr_inline(*this);
   }
-  __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
-  __device__ __forceinline__ Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+  __device__ __forceinline__ Fq2T dbl() const { return {c0.dbl(), c1.dbl()}; }
+  __device__ __forceinline__ Fq2T neg() const { return {c0.neg(), c1.neg()}; }
   __device__ __forceinline__ bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
   __device__ __forceinline__ bool raw_is_zero() const {
     return c0.raw_is_zero() && c1.raw_is_zero();
   }
-  __device__ __forceinline__ friend bool operator==(const Fq2& a, const Fq2& b) {
+  __device__ __forceinline__ friend bool operator==(const Fq2T& a, const Fq2T& b) {
     return (a - b).is_zero();
   }
-  __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
-  __device__ __forceinline__ Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
-  __device__ __forceinline__ Fq2 reduced() const { return {c0.reduced(), c1.reduced()}; }
-  __device__ Fq2 inverse() const {
+  __device__ __forceinline__ Fq2T to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
+  __device__ __forceinline__ Fq2T from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
+  __device__ __forceinline__ Fq2T reduced() const { return {c0.reduced(), c1.reduced()}; }
+  __device__ Fq2T inverse() const {
     Fq d = (c0.sqr() + c1.sqr()).inverse();
     return {c0 * d, (c1 * d).neg()};
   }
 };
+using Fq2 = Fq2T<false>;
+using Fq2C = Fq2T<true>;
 
 // ---------------------------------------------------------------- Fq2 split over a lane pair
 // One Fq2 element held by TWO adjacent lanes of a warp: the even lane owns c0, the odd lane c1.
