@@ -294,7 +294,7 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, boo
   if (second_set) ZKB_CUDA(ctx, s.buckets2.ensure(p.n_buckets * p.point_bytes));
   b->buckets2 = s.buckets2.p;
   b->flag = (uint32_t*)s.flag.p;
-  ZKB_CUDA(ctx, s.keys_in.ensure(p.m * 4));
+  ZKB_CUDA(ctx, s.keys_in.ensure(p.m * 8));    // 8 B per entry: the bucket sort's intermediate (key, value) array
   ZKB_CUDA(ctx, s.vals_in.ensure(p.m * 4));
   ZKB_CUDA(ctx, s.keys_out.ensure(p.m * 4));
   ZKB_CUDA(ctx, s.vals_out.ensure(p.m * 4));
@@ -890,12 +890,20 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
     ctx->msm_host_chunks = value;
     return ZKB_OK;
   }
+  if (!std::strcmp(key, "assemble_on_device")) {
+    ctx->assemble_on_device = value ? 1 : 0;
+    return ZKB_OK;
+  }
   if (!std::strcmp(key, "pk_precompute")) {
     ctx->pk_precompute = value ? 1 : 0;
     return ZKB_OK;
   }
   if (!std::strcmp(key, "comm_force_staging")) {   // before the first distributed call
     ctx->comm_force_staging = value ? 1 : 0;
+    return ZKB_OK;
+  }
+  if (!std::strcmp(key, "msm_sort")) {        // process-wide: 0 = hand-written bucket sort, 1 = cub radix sort
+    msm_set_sort_mode(value ? 1 : 0);
     return ZKB_OK;
   }
   if (!std::strcmp(key, "msm_g2_pair")) {     // process-wide comparison switch, see msm_g2.cu

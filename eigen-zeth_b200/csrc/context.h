@@ -82,6 +82,7 @@ struct zkb_ctx {
   int64_t msm_profile = 0;
   int64_t msm_host_chunks = 0;             // 0 = auto
   int64_t pk_precompute = 1;               // proving-key queries carry precomputed window multiples
+  int64_t assemble_on_device = 0;          // 1: the one-CTA assembly kernel instead of the host ladders (comparison)
   cudaStream_t copy_stream = nullptr;      // H2D of scalar chunks, overlapped with compute
   cudaEvent_t copy_ev[16] = {};
   cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -149,6 +150,11 @@ int bases_download_nolock(zkb_ctx* ctx, const zkb_bases* b, uint64_t first, uint
                           uint8_t* out);
 
 void host_fr_root(uint32_t log_n, int inverse, uint32_t out_mont[8]);
+// proof assembly on the host (verify.cpp): fixed = alpha_g1 | beta_g1 | delta_g1 | beta_g2 | delta_g2 canonical
+bool host_groth16_assemble(const uint8_t fixed[448], const uint8_t sums[ZKB_INTERMEDIATE_BYTES], const uint8_t r[32],
+                           const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES], const void* tables);
+void* host_assemble_tables_create(const uint8_t fixed[448]);   // window tables of the key's delta_g1 / delta_g2
+void host_assemble_tables_free(void* t);
 
 // ---- distributed building blocks (dist.cu); collective over ctx->comm
 // one four-step transform of this rank's layout-`d` block x (n / world elements, Montgomery) into

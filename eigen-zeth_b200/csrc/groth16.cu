@@ -9,6 +9,7 @@
 
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <new>
@@ -29,6 +30,8 @@ struct zkb_pk {
   // fixed points, affine Montgomery, device: alpha_g1 | beta_g1 | delta_g1 (3 x 64 B) and
   // beta_g2 | delta_g2 (2 x 128 B)
   void* d_fixed = nullptr;
+  uint8_t h_fixed[448] = {};         // the same five points, canonical bytes, for the host-side assembly
+  mutable void* h_tables = nullptr;  // fixed-base window tables of delta_g1 / delta_g2 (built at first use)
   // CSR matrices A, B, C (device)
   uint32_t* d_row_ptr[3] = {nullptr, nullptr, nullptr};
   uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
@@ -321,6 +324,7 @@ void zkb_pk_free(zkb_pk* pk) {
     if (pk->d_cidx[k]) cudaFree(pk->d_cidx[k]);
   }
   cudaSetDevice(cur);
+  host_assemble_tables_free(pk->h_tables);
   delete pk;
 }
 
@@ -534,6 +538,8 @@ int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint3
     zkb_bases_free(b2);
     if (e != cudaSuccess) throw cuda_fail(ctx, e, "fixed points");
     if (r1 || r2) throw (r1 ? r1 : r2);
+    std::memcpy(pk->h_fixed, g1c, 192);
+    std::memcpy(pk->h_fixed + 192, g2c, 256);
     std::memcpy(vk_out, g1c, 64);
     std::memcpy(vk_out + 64, g2c, 128);
     std::memcpy(vk_out + 192, g2c + 256, 128);
@@ -657,6 +663,8 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     uint8_t f1[192], f2[256];
     std::memcpy(f1, d->alpha_g1, 64); std::memcpy(f1 + 64, d->beta_g1, 64); std::memcpy(f1 + 128, d->delta_g1, 64);
     std::memcpy(f2, d->beta_g2, 128); std::memcpy(f2 + 128, d->delta_g2, 128);
+    std::memcpy(pk->h_fixed, f1, 192);
+    std::memcpy(pk->h_fixed + 192, f2, 256);
     zkb_bases *b1 = nullptr, *b2 = nullptr;
     if ((rc = bases_from_bytes(ctx, f1, 3, 0, 0, &b1))) throw rc;
     if ((rc = bases_from_bytes(ctx, f2, 2, 0, 1, &b2))) { zkb_bases_free(b1); throw rc; }
@@ -763,6 +771,22 @@ static int prove_assemble_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t r[
   ok = ok && HFr::lt_mod(w);
   if (!ok) return set_error(ctx, ZKB_EINVAL, "non-canonical r / s");
   cudaStream_t st = ctx->stream;
+  if (!ctx->assemble_on_device) {
+    // the five sums come home (384 bytes) and the ladders run on host cores: see host_groth16_assemble
+    uint8_t sums[ZKB_INTERMEDIATE_BYTES];
+    auto t0 = std::chrono::steady_clock::now();
+    ZKB_CUDA(ctx, cudaMemcpyAsync(sums, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "groth16 msm phase");
+    auto t1 = std::chrono::steady_clock::now();
+    if (!pk->h_tables) pk->h_tables = host_assemble_tables_create(pk->h_fixed);   // null on failure: plain ladders
+    if (!host_groth16_assemble(pk->h_fixed, sums, r, s, proof_out, pk->h_tables))
+      return set_error(ctx, ZKB_EINVAL, "malformed MSM sums / key constants in the proof assembly");
+    if (ms_opt) *ms_opt = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    (void)t0;
+    return ZKB_OK;
+  }
   cudaEvent_t e0, e1;
   ZKB_CUDA(ctx, cudaEventCreate(&e0));
   ZKB_CUDA(ctx, cudaEventCreate(&e1));

@@ -22,6 +22,8 @@ struct MsmPlan {
   uint64_t m;               // n * nwin (key, value) pairs
   int key_bits;             // radix-sort key width
   int g2_pair;              // G2 only: level-1 walk splits one Fq2 point operation over a lane pair
+  int sort_mode;            // 0 = hand-written bucket sort, 1 = cub radix sort
+  int sm_count;
   uint32_t l1_threads;      // chunks of the level-1 walk
   uint32_t l2_len;          // chunk length of the level-2 walk
   uint32_t l2_threads;
@@ -29,6 +31,13 @@ struct MsmPlan {
   uint64_t red_run_total;   // points of run output over all levels and sets
   size_t point_bytes;       // sizeof(XYZZ)
   size_t sort_temp_bytes;
+};
+
+struct SortPlan {            // geometry of the hand-written bucket sort (msm_sort.cu)
+  uint32_t lo_bits;          // fine bucket bits inside a coarse bin
+  uint32_t n_coarse;         // coarse bins
+  uint32_t max_items;        // upper bound of pass-C work items
+  uint64_t fine_entries;     // n_coarse << lo_bits
 };
 
 struct MsmBuffers {
@@ -66,6 +75,16 @@ void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin,
 // (>= r) raise bit 0 of *d_flag.
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                          uint32_t idx_base, cudaStream_t s);
+// the same contract, hand-written: digit extraction fused with a two-level MSD bucket sort (msm_sort.cu);
+// needs b.keys_in of 8 bytes per entry and b.sort_temp of msm_sort_scratch_bytes(p)
+void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                                uint32_t idx_base, int sm_count, cudaStream_t s);
+SortPlan msm_sort_plan(const MsmPlan& p);
+size_t msm_sort_scratch_bytes(const MsmPlan& p);
+// process-wide switch (zkb_ctx_set "msm_sort"): 0 = the bucket sort above (default), 1 = digits kernel +
+// cub::DeviceRadixSort (library baseline, kept for comparison)
+void msm_set_sort_mode(int mode);
+int msm_get_sort_mode();
 void msm_accumulate_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
                        cudaStream_t s);
 void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,

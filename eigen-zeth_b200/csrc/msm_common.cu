@@ -14,6 +14,9 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launches(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 static std::atomic<int> g_g2_pair{0};   // measured on B200: the lane-pair walk is 5 % slower
+static std::atomic<int> g_sort_mode{0};
+void msm_set_sort_mode(int mode) { g_sort_mode.store(mode ? 1 : 0); }
+int msm_get_sort_mode() { return g_sort_mode.load(); }
 void msm_set_g2_pair(int on) { g_g2_pair.store(on ? 1 : 0); }
 int msm_get_g2_pair() { return g_g2_pair.load(); }
 
@@ -116,6 +119,8 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
   while ((1ull << p.key_bits) <= p.n_buckets) p.key_bits++;   // sentinel == n_buckets must fit
   // level-1 threads: one resident wave, never less than 8 entries per thread
   p.g2_pair = is_g2 ? msm_get_g2_pair() : 0;
+  p.sort_mode = msm_get_sort_mode();
+  p.sm_count = sm_count;
   uint32_t per_sm = is_g2 ? msm_l1_threads_per_sm_g2(p.g2_pair) : msm_l1_threads_per_sm_g1();
   uint64_t t1 = uint64_t(sm_count) * per_sm;
   uint64_t cap = (p.m + 7) / 8;
@@ -134,12 +139,18 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
   }
   p.point_bytes = is_g2 ? 256 : 128;
   p.sort_temp_bytes = msm_sort_temp_bytes(p.m, p.key_bits);
+  const size_t own = msm_sort_scratch_bytes(p);
+  if (own > p.sort_temp_bytes) p.sort_temp_bytes = own;
   return p;
 }
 
 
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                          uint32_t idx_base, cudaStream_t s) {
+  if (p.sort_mode == 0) {
+    msm_digits_and_bucket_sort(p, b, d_scalars, n, idx_base, p.sm_count, s);
+    return;
+  }
   if (b.ev) cudaEventRecord(b.ev[0], s);
   uint32_t blocks = uint32_t((n + 255) / 256);
   if (blocks)

@@ -1,0 +1,385 @@
+// msm_sort.cu — K5: scalars -> (bucket key, point index) pairs grouped by bucket, hand-written.
+//
+// No reference counterpart.  The walk (msm_impl.cuh) only needs entries of one
+// bucket to be CONTIGUOUS and buckets to appear in key order; it does not need a stable sort.  That
+// allows a two-level MSD bucket sort fused with the digit extraction, instead of digits -> 16 B per
+// entry in HBM -> a generic 3-pass LSD radix sort:
+//
+//   A  histogram   read the scalars, recompute every signed digit, count entries per COARSE bin
+//                  (key >> lo_bits) in shared memory, one global atomic per (tile, bin).
+//   P  plan        one CTA: exclusive scan of the coarse histogram (= where each bin starts in the
+//                  output AND in the intermediate array), m_valid, and the work list of pass C:
+//                  one item per bin, or several per bin when a bin is larger than a CTA can hold.
+//   B  scatter     read the scalars again (L2), recompute the digits, reserve room per (tile, bin)
+//                  with one global atomic, write (key, value) into the bin's region.  Every bin has
+//                  ONE moving write frontier, so the set of partially written lines is H x 128 B —
+//                  far below the 126 MB L2, which merges the short runs before they reach HBM.
+//   C  bucketize   one CTA per work item loads its segment (<= kCap entries, 8 B each) into shared
+//                  memory, counts the fine buckets (key & (2^lo_bits - 1)), scans, and writes every
+//                  entry to its final position; a whole bin is one CTA's private output region, so
+//                  its scattered 4-byte writes also complete whole lines inside L2.
+//                  Oversized bins (skewed scalars: 0/1 witnesses, all-equal scalars) are cut into
+//                  segments that first add their fine histograms into a global table (C1), get their
+//                  bucket offsets from a per-bin scan (C1s) and reserve output ranges with global
+//                  atomics (C2) — same result, any distribution.
+// Zero digits are never emitted (no sentinel key, no count kernel).  HBM traffic per entry: 8 B
+// written + 8 B read + 8 B written, plus 2 x 32 B per scalar — against 16 B + 3 x 16 B + histogram
+// for digits + cub::DeviceRadixSort.  The order inside a bucket is not deterministic; the bucket SUM
+// is, and results are compared in canonical affine form.
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "msm.h"
+
+namespace zkb {
+
+constexpr uint32_t kSortThreads = 512;
+constexpr uint32_t kPlaceThreads = 1024;
+constexpr uint32_t kCap = 20480;            // entries a pass-C CTA holds in shared memory (160 KB)
+constexpr uint32_t kMaxCoarse = 16384;      // coarse bins (64 KB of shared counters in passes A / B)
+constexpr uint32_t kMaxFine = 4096;         // fine buckets per coarse bin
+
+// signed-digit extraction shared by passes A and B (same recoding as msm_digits_kernel)
+struct DigitCfg {
+  uint32_t c, nwin, half, mask, val_stride, idx_base, one_set;
+};
+
+__device__ __forceinline__ bool scalar_is_canonical(const uint32_t (&s)[9]) {
+  const uint32_t rmod[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                            0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  bool lt = false, decided = false;
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    if (!decided && s[k] != rmod[k]) {
+      lt = s[k] < rmod[k];
+      decided = true;
+    }
+  }
+  return lt;
+}
+
+// calls f(key, val) for every non-zero digit of scalar i
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ scalars, uint64_t i, const DigitCfg& d,
+                                               uint32_t* flag, bool check, Fn f) {
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+  if (check && !scalar_is_canonical(s)) atomicOr(flag, 1u);
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < d.nwin; w++) {
+    uint32_t bit = w * d.c;
+    uint32_t word = bit >> 5, sh = bit & 31;
+    uint32_t dg = 0;
+    if (word < 8) {
+      uint64_t two = (uint64_t(s[word + 1]) << 32) | s[word];
+      dg = uint32_t(two >> sh) & d.mask;
+    }
+    dg += carry;
+    uint32_t neg = dg > d.half;
+    uint32_t mag = neg ? (1u << d.c) - dg : dg;
+    carry = neg;
+    if (mag) {
+      uint32_t key = (d.one_set ? 0u : w * d.half) + (mag - 1);
+      uint32_t val = (w * d.val_stride + d.idx_base + uint32_t(i)) | (neg << 31);
+      f(key, val);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- A: coarse histogram
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
+                                                                 DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
+                                                                 uint32_t per_cta, uint32_t* __restrict__ coarse_hist,
+                                                                 uint32_t* __restrict__ flag) {
+  extern __shared__ uint32_t sm_cnt[];
+  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) sm_cnt[b] = 0;
+  __syncthreads();
+  const uint64_t first = uint64_t(blockIdx.x) * per_cta;
+  const uint64_t last = first + per_cta < n ? first + per_cta : n;
+  for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
+    for_each_digit(scalars, i, d, flag, true, [&](uint32_t key, uint32_t) { atomicAdd(&sm_cnt[key >> lo_bits], 1u); });
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) {
+    uint32_t v = sm_cnt[b];
+    if (v) atomicAdd(&coarse_hist[b], v);
+  }
+}
+
+// ---------------------------------------------------------------- P: plan (one CTA)
+// in: coarse_hist[n_coarse].  out: coarse_off[n_coarse + 1] (exclusive scan), cursor[b] = coarse_off[b]
+// (pass B's write frontiers), m_valid, items[] = (bin, segment) for pass C, n_items, and
+// bin_flags[b] = 1 for bins cut into several segments.
+__global__ void __launch_bounds__(1024) sort_plan_kernel(const uint32_t* __restrict__ coarse_hist, uint32_t n_coarse,
+                                                         uint32_t* __restrict__ coarse_off, uint32_t* __restrict__ cursor,
+                                                         uint64_t* __restrict__ m_valid, uint2* __restrict__ items,
+                                                         uint32_t* __restrict__ n_items, uint32_t* __restrict__ bin_multi) {
+  __shared__ uint32_t s_sum[1024], s_seg[1024];
+  const uint32_t t = threadIdx.x, per = (n_coarse + 1023) / 1024;
+  const uint32_t lo = t * per, hi = lo + per < n_coarse ? lo + per : n_coarse;
+  uint32_t sum = 0, segs = 0;
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t v = coarse_hist[b];
+    sum += v;
+    segs += (v + kCap - 1) / kCap;
+  }
+  s_sum[t] = sum;
+  s_seg[t] = segs;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials (both arrays)
+  for (uint32_t o = 1; o < 1024; o <<= 1) {
+    uint32_t a = t >= o ? s_sum[t - o] : 0, b2 = t >= o ? s_seg[t - o] : 0;
+    __syncthreads();
+    s_sum[t] += a;
+    s_seg[t] += b2;
+    __syncthreads();
+  }
+  uint32_t off = s_sum[t] - sum, item = s_seg[t] - segs;
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t v = coarse_hist[b];
+    coarse_off[b] = off;
+    cursor[b] = off;
+    uint32_t ns = (v + kCap - 1) / kCap;
+    bin_multi[b] = ns > 1;
+    for (uint32_t s = 0; s < ns; s++) items[item + s] = make_uint2(b, s);
+    item += ns;
+    off += v;
+  }
+  if (t == 1023) {
+    coarse_off[n_coarse] = s_sum[1023];
+    *m_valid = s_sum[1023];
+    *n_items = s_seg[1023];
+  }
+}
+
+// ---------------------------------------------------------------- B: scatter into coarse bins
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
+                                                                    DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
+                                                                    uint32_t per_cta, uint32_t* __restrict__ cursor,
+                                                                    uint2* __restrict__ mid) {
+  extern __shared__ uint32_t sm_cnt[];
+  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) sm_cnt[b] = 0;
+  __syncthreads();
+  const uint64_t first = uint64_t(blockIdx.x) * per_cta;
+  const uint64_t last = first + per_cta < n ? first + per_cta : n;
+  for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
+    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t) { atomicAdd(&sm_cnt[key >> lo_bits], 1u); });
+  __syncthreads();
+  // reserve this tile's room in every bin it touches; the slot then holds the next write position
+  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) {
+    uint32_t v = sm_cnt[b];
+    if (v) sm_cnt[b] = atomicAdd(&cursor[b], v);
+  }
+  __syncthreads();
+  for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
+    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t val) {
+      uint32_t pos = atomicAdd(&sm_cnt[key >> lo_bits], 1u);
+      mid[pos] = make_uint2(key, val);
+    });
+}
+
+// ---------------------------------------------------------------- C1: fine histograms of oversized bins
+__global__ void __launch_bounds__(kSortThreads) sort_fine_hist_kernel(const uint2* __restrict__ mid,
+                                                                      const uint32_t* __restrict__ coarse_off,
+                                                                      const uint2* __restrict__ items,
+                                                                      const uint32_t* __restrict__ n_items,
+                                                                      const uint32_t* __restrict__ bin_multi,
+                                                                      uint32_t lo_bits, uint32_t* __restrict__ fine) {
+  __shared__ uint32_t cnt[kMaxFine];
+  for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
+    const uint2 w = items[it];
+    if (!bin_multi[w.x]) continue;
+    const uint32_t L = 1u << lo_bits, mask = L - 1;
+    for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) cnt[f] = 0;
+    __syncthreads();
+    const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
+    const uint32_t s0 = b0 + w.y * kCap, s1 = s0 + kCap < b1 ? s0 + kCap : b1;
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) atomicAdd(&cnt[mid[i].x & mask], 1u);
+    __syncthreads();
+    for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) {
+      uint32_t v = cnt[f];
+      if (v) atomicAdd(&fine[(uint64_t(w.x) << lo_bits) + f], v);
+    }
+    __syncthreads();
+  }
+}
+
+// C1s: per oversized bin, fine counts -> output cursors (exclusive scan + the bin's base)
+__global__ void __launch_bounds__(1024) sort_fine_scan_kernel(const uint32_t* __restrict__ coarse_off,
+                                                              const uint32_t* __restrict__ bin_multi, uint32_t n_coarse,
+                                                              uint32_t lo_bits, uint32_t* __restrict__ fine) {
+  __shared__ uint32_t part[1024];
+  for (uint32_t b = blockIdx.x; b < n_coarse; b += gridDim.x) {
+    if (!bin_multi[b]) continue;
+    const uint32_t L = 1u << lo_bits, per = (L + 1023) / 1024, t = threadIdx.x;
+    uint32_t* f = fine + (uint64_t(b) << lo_bits);
+    const uint32_t lo = t * per, hi = lo + per < L ? lo + per : L;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += f[i];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+      uint32_t a = t >= o ? part[t - o] : 0;
+      __syncthreads();
+      part[t] += a;
+      __syncthreads();
+    }
+    uint32_t off = coarse_off[b] + part[t] - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+      uint32_t v = f[i];
+      f[i] = off;
+      off += v;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- C2: final placement
+__global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* __restrict__ mid,
+                                                                  const uint32_t* __restrict__ coarse_off,
+                                                                  const uint2* __restrict__ items,
+                                                                  const uint32_t* __restrict__ n_items,
+                                                                  const uint32_t* __restrict__ bin_multi, uint32_t lo_bits,
+                                                                  uint32_t* __restrict__ fine, uint32_t* __restrict__ keys_out,
+                                                                  uint32_t* __restrict__ vals_out) {
+  extern __shared__ uint2 sm_ent[];                          // kCap entries, then 2^lo_bits counters
+  uint32_t* pos = reinterpret_cast<uint32_t*>(sm_ent + kCap);
+  __shared__ uint32_t part[kPlaceThreads];
+  for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
+    const uint2 w = items[it];
+    const uint32_t L = 1u << lo_bits, mask = L - 1, t = threadIdx.x;
+    for (uint32_t f = t; f < L; f += blockDim.x) pos[f] = 0;
+    __syncthreads();
+    const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
+    const uint32_t s0 = b0 + w.y * kCap, s1 = s0 + kCap < b1 ? s0 + kCap : b1, cnt = s1 - s0;
+    for (uint32_t i = t; i < cnt; i += blockDim.x) {
+      uint2 e = mid[s0 + i];
+      sm_ent[i] = e;
+      atomicAdd(&pos[e.x & mask], 1u);
+    }
+    __syncthreads();
+    if (bin_multi[w.x]) {
+      // shared bin: reserve this segment's share of every fine bucket in the global cursors
+      for (uint32_t f = t; f < L; f += blockDim.x) {
+        uint32_t v = pos[f];
+        pos[f] = v ? atomicAdd(&fine[(uint64_t(w.x) << lo_bits) + f], v) : 0;
+      }
+    } else {
+      // private bin: exclusive scan of the fine counts, based at the bin's start
+      const uint32_t per = (L + kPlaceThreads - 1) / kPlaceThreads;
+      const uint32_t lo = t * per, hi = lo + per < L ? lo + per : L;
+      uint32_t sum = 0;
+      for (uint32_t f = lo; f < hi && f < L; f++) sum += pos[f];
+      part[t] = sum;
+      __syncthreads();
+      for (uint32_t o = 1; o < kPlaceThreads; o <<= 1) {
+        uint32_t a = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += a;
+        __syncthreads();
+      }
+      uint32_t off = b0 + part[t] - sum;
+      for (uint32_t f = lo; f < hi && f < L; f++) {
+        uint32_t v = pos[f];
+        pos[f] = off;
+        off += v;
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = t; i < cnt; i += blockDim.x) {
+      uint2 e = sm_ent[i];
+      uint32_t p = atomicAdd(&pos[e.x & mask], 1u);
+      keys_out[p] = e.x;
+      vals_out[p] = e.y;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static uint32_t pow2_ceil(uint64_t x) {
+  uint32_t b = 0;
+  while ((1ull << b) < x) b++;
+  return b;
+}
+
+SortPlan msm_sort_plan(const MsmPlan& p) {
+  SortPlan s{};
+  const uint32_t kb = pow2_ceil(p.n_buckets);              // key space rounded up to a power of two
+  // coarse bins: average fill <= kCap / 3 so that private bins are the rule, and few enough for the
+  // shared counters of passes A / B; fine buckets per bin <= kMaxFine
+  uint32_t hb = pow2_ceil((p.m + kCap / 3 - 1) / (kCap / 3));
+  const uint32_t hb_min = kb > 12 ? kb - 12 : 0, hb_max = 14;
+  if (hb < hb_min) hb = hb_min;
+  if (hb > hb_max) hb = hb_max;
+  if (hb > kb) hb = kb;
+  s.lo_bits = kb - hb;
+  s.n_coarse = 1u << hb;
+  s.max_items = s.n_coarse + uint32_t(p.m / kCap) + 1;
+  s.fine_entries = uint64_t(s.n_coarse) << s.lo_bits;
+  return s;
+}
+
+size_t msm_sort_scratch_bytes(const MsmPlan& p) {
+  SortPlan s = msm_sort_plan(p);
+  // coarse_hist | coarse_off (+1) | cursor | bin_multi | n_items | items | fine
+  return size_t(s.n_coarse) * 4 * 4 + 64 + size_t(s.max_items) * 8 + s.fine_entries * 4 + 256;
+}
+
+void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
+                                uint32_t idx_base, int sm_count, cudaStream_t st) {
+  const SortPlan s = msm_sort_plan(p);
+  const size_t place_smem = size_t(kCap) * 8 + (size_t(4) << s.lo_bits);
+  // opt-in to large dynamic shared memory, once per device of this process
+  static std::once_flag configured[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(configured[dev & 63], [] {
+    cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxFine * 4));
+    cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxCoarse * 4));
+    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxCoarse * 4));
+  });
+  if (b.ev) cudaEventRecord(b.ev[0], st);
+  char* sc = reinterpret_cast<char*>(b.sort_temp);
+  uint32_t* coarse_hist = reinterpret_cast<uint32_t*>(sc);
+  uint32_t* coarse_off = coarse_hist + s.n_coarse;
+  uint32_t* cursor = coarse_off + s.n_coarse + 1;
+  uint32_t* bin_multi = cursor + s.n_coarse;
+  uint32_t* n_items = bin_multi + s.n_coarse;
+  uint2* items = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(n_items + 4) + 15) & ~uintptr_t(15));
+  uint32_t* fine = reinterpret_cast<uint32_t*>(items + s.max_items);
+  uint2* mid = reinterpret_cast<uint2*>(b.keys_in);          // 8 bytes per entry (ensure_msm_buffers)
+  cudaMemsetAsync(coarse_hist, 0, size_t(s.n_coarse) * 4, st);
+  cudaMemsetAsync(fine, 0, s.fine_entries * 4, st);
+  DigitCfg d;
+  d.c = uint32_t(p.c);
+  d.nwin = p.nwin;
+  d.half = p.half;
+  d.mask = (1u << p.c) - 1;
+  d.val_stride = uint32_t(p.val_stride);
+  d.idx_base = idx_base;
+  d.one_set = p.val_stride != 0;
+  // tiles of passes A / B: enough entries per tile for the per-bin reservations to aggregate
+  // (>= 8 per coarse bin), and at least two waves of CTAs on large inputs
+  uint64_t per_cta = (uint64_t(8) * s.n_coarse + p.nwin - 1) / p.nwin;
+  if (per_cta < 2048) per_cta = 2048;
+  uint32_t tiles = uint32_t((n + per_cta - 1) / per_cta);
+  if (!tiles) tiles = 1;
+  const size_t csm = size_t(s.n_coarse) * 4;
+  sort_hist_kernel<<<tiles, kSortThreads, csm, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits,
+                                                     s.n_coarse, uint32_t(per_cta), coarse_hist, b.flag);
+  sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items, bin_multi);
+  sort_scatter_kernel<<<tiles, kSortThreads, csm, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits,
+                                                        s.n_coarse, uint32_t(per_cta), cursor, mid);
+  if (b.ev) cudaEventRecord(b.ev[1], st);
+  const uint32_t grid_c = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;
+  sort_fine_hist_kernel<<<grid_c, kSortThreads, 0, st>>>(mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine);
+  sort_fine_scan_kernel<<<s.n_coarse < 296 ? s.n_coarse : 296, 1024, 0, st>>>(coarse_off, bin_multi, s.n_coarse, s.lo_bits, fine);
+  sort_place_kernel<<<uint32_t(sm_count) < s.max_items ? uint32_t(sm_count) : s.max_items, kPlaceThreads, place_smem, st>>>(
+      mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine, b.keys_out, b.vals_out);
+  count_launches(6);
+  if (b.ev) cudaEventRecord(b.ev[2], st);
+}
+
+}  // namespace zkb

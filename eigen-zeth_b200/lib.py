@@ -32,6 +32,7 @@ EXPORTS = [
     "zkb_comm_transport", "zkb_comm_barrier", "zkb_comm_destroy", "zkb_fr_ntt_dist_dev",
     "zkb_fr_index_power_table_dist", "zkb_msm_g1_dist_dev", "zkb_msm_g2_dist_dev", "zkb_msm_g1_dist",
     "zkb_msm_g2_dist", "zkb_pk_synthetic_dist", "zkb_groth16_prove_dist", "zkb_selftest_final_exp",
+    "zkb_groth16_assemble_host", "zkb_selftest_assemble_tables",
 ]
 COMM_ID_BYTES = 128
 
@@ -135,6 +136,8 @@ def load_library() -> C.CDLL:
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
         lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
         lib.zkb_selftest_final_exp.argtypes = [u8p]
+        lib.zkb_groth16_assemble_host.argtypes = [u8p, u8p, u8p, u8p, vp]
+        lib.zkb_selftest_assemble_tables.argtypes = [u8p, u8p, u8p, u8p]
     lib.zkb_comm_unique_id.argtypes = [vp]
     lib.zkb_comm_init.argtypes = [vp, u8p, i32, i32]
     lib.zkb_comm_init_local.argtypes = [C.POINTER(vp), i32]
@@ -638,6 +641,18 @@ def synthetic_witness_into(log_n: int, w0: bytes, w1: bytes, ptr: int):
     rc = load_library().zkb_synthetic_witness(log_n, w0, w1, C.c_void_p(ptr))
     if rc:
         raise ZkbError(rc, "zkb_synthetic_witness failed")
+
+
+def groth16_assemble_host(fixed: dict, sums: bytes, r: bytes, s: bytes) -> bytes:
+    """five MSM sums + the key's fixed points (alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2) + (r, s) -> proof"""
+    blob = fixed["alpha_g1"] + fixed["beta_g1"] + fixed["delta_g1"] + fixed["beta_g2"] + fixed["delta_g2"]
+    if len(blob) != 448 or len(sums) != INTERMEDIATE_BYTES:
+        raise ValueError("fixed points must total 448 bytes, sums 384")
+    out = C.create_string_buffer(PROOF_BYTES)
+    rc = load_library().zkb_groth16_assemble_host(blob, bytes(sums), r, s, out)
+    if rc:
+        raise ZkbError(rc, "zkb_groth16_assemble_host: malformed input")
+    return out.raw
 
 
 def groth16_verify(vk: bytes, proof: bytes, public_input: bytes) -> bool:

@@ -129,9 +129,11 @@ class GpuGroth16Backend:
             self.group = lib.DeviceGroup(devices)                   # one context + NCCL rank per GPU
             self.group.pk_synthetic(log_n, setup_seed)
             self._vk = self.group.vk
-        self._buf = [_PinnedWitness(lib, 32 << log_n) for _ in range(2)]
-        self._next = 0
-        self._pre = None                                           # (key, thread, buffer)
+        # witness staging: a small pool of pinned buffers, each either free, being filled by a
+        # generator thread for one (recursive_proof, aggregator) key, or in use by a running proof
+        self._slots = [{"buf": _PinnedWitness(lib, 32 << log_n), "key": None, "thread": None, "in_use": False, "age": 0}
+                       for _ in range(2)]
+        self._age = 0
         self._pre_lock = threading.Lock()
         log.info("proving key for 2^%d constraints resident on GPU(s) %s (%.1f s)", log_n, devices, time.time() - t0)
 
@@ -143,36 +145,61 @@ class GpuGroth16Backend:
     def _witness_seeds(self, recursive_proof, aggregator_addr):
         return _fr_from_hash("w0", recursive_proof, aggregator_addr), _fr_from_hash("w1", recursive_proof, aggregator_addr)
 
+    def _claim_slot(self, key):
+        """under the lock: the slot already holding `key`, else a reusable one (idle generator, no proof
+        running on it) re-targeted to `key` with its generator started; None when every slot is busy"""
+        for sl in self._slots:
+            if sl["key"] == key:
+                return sl
+        idle = [sl for sl in self._slots if not sl["in_use"] and (sl["thread"] is None or not sl["thread"].is_alive())]
+        if not idle:
+            return None
+        sl = min(idle, key=lambda x: (x["key"] is not None, x["age"]))       # a free one first, else the oldest
+        w0, w1 = self._witness_seeds(*key)
+        sl["key"] = key
+        self._age += 1
+        sl["age"] = self._age
+        sl["thread"] = threading.Thread(target=self.lib.synthetic_witness_into, args=(self.log_n, w0, w1, sl["buf"].ptr),
+                                        daemon=True)
+        sl["thread"].start()
+        return sl
+
     def prefetch(self, recursive_proof: str, aggregator_addr: str):
-        """Start generating the witness for (recursive_proof, aggregator_addr) in the background.  The
-        servicer calls this when it hands out an aggregated proof: the client sends that very string
-        back as GenFinalProofRequest.recursive_proof one step (>= 1 s, provider.rs:542) later."""
-        key = (recursive_proof, aggregator_addr)
+        """Start generating the witness for (recursive_proof, aggregator_addr) in the background (no-op
+        when it is already under way or every staging buffer is busy).  The servicer calls this as
+        soon as the string is known — at the chunk step, three client sleeps (provider.rs:542) ahead
+        of the GenFinalProof request that carries it."""
         with self._pre_lock:
-            if self._pre and self._pre[0] == key:
-                return
-            buf = self._buf[self._next]
-            self._next ^= 1
-            w0, w1 = self._witness_seeds(*key)
-            th = threading.Thread(target=self.lib.synthetic_witness_into, args=(self.log_n, w0, w1, buf.ptr), daemon=True)
-            self._pre = (key, th, buf)
-            th.start()
+            self._claim_slot((recursive_proof, aggregator_addr))
 
     def _witness(self, recursive_proof, aggregator_addr):
+        """-> the slot holding this witness, generator finished, marked in use"""
         key = (recursive_proof, aggregator_addr)
-        with self._pre_lock:
-            pre = self._pre if self._pre and self._pre[0] == key else None
-        if pre is None:
-            self.prefetch(recursive_proof, aggregator_addr)
+        while True:
             with self._pre_lock:
-                pre = self._pre
-        pre[1].join()
-        return pre[2]
+                sl = self._claim_slot(key)
+                if sl is not None:
+                    sl["in_use"] = True
+                    break
+            time.sleep(0.001)            # every buffer is busy with another stream's proof: wait for one
+        sl["thread"].join()
+        return sl
+
+    def _release(self, sl):
+        with self._pre_lock:
+            sl["in_use"] = False
+            sl["key"] = None             # a replayed batch is answered from the servicer's cache, not from here
 
     def final_proof(self, batch_id: str, recursive_proof: str, aggregator_addr: str):
         t = {}
         t0 = time.perf_counter()
-        wbuf = self._witness(recursive_proof, aggregator_addr)
+        slot = self._witness(recursive_proof, aggregator_addr)
+        try:
+            return self._final_proof_on(slot["buf"], t, t0, batch_id, recursive_proof, aggregator_addr)
+        finally:
+            self._release(slot)
+
+    def _final_proof_on(self, wbuf, t, t0, batch_id, recursive_proof, aggregator_addr):
         t["witness_wait_ms"] = 1e3 * (time.perf_counter() - t0)
         r = _blinding(self.secret, "r", batch_id, recursive_proof, aggregator_addr)
         s = _blinding(self.secret, "s", batch_id, recursive_proof, aggregator_addr)
@@ -195,8 +222,10 @@ class GpuGroth16Backend:
         return proof_json, input_json, t
 
     def close(self):
-        for b in self._buf:
-            b.free()
+        for sl in self._slots:
+            if sl["thread"] is not None:
+                sl["thread"].join()
+            sl["buf"].free()
 
 
 class BatchLedger:
@@ -270,6 +299,11 @@ class ProverServicer:
             return pb.GenBatchProofResponse(gen_batch_chunks=pb.GenBatchChunksResult(
                 batch_id=req.batch_id, result_code=pb.COMPLETED_ERROR, error_message=bad,
                 pre_state_root=bytes(32), post_state_root=bytes(32)))
+        # Everything the later steps hand out is a deterministic function of what is known now, so the
+        # string that will come back as GenFinalProofRequest.recursive_proof three steps (>= 3 s of
+        # client sleeps, provider.rs:542) from now is already known: start the witness generation of
+        # the final circuit here and it is off the GenFinalProof critical path whatever its size.
+        self._prefetch(self._aggregated(self._chunk_proof_strings(req.batch_id, batch_data, 2)))
         res = pb.GenBatchChunksResult(
             batch_id=req.batch_id, task_id=task_id, result_code=pb.COMPLETED_OK, chunk_count=2, batch_data=batch_data,
             pre_state_root=_h("pre", req.chain_id, *blocks), post_state_root=_h("post", req.chain_id, *blocks))
@@ -282,24 +316,39 @@ class ProverServicer:
             return pb.GenBatchProofResponse(gen_chunk_proof=pb.GenChunkProofResult(
                 batch_id=req.batch_id, task_id=req.task_id, result_code=pb.COMPLETED_ERROR, error_message=bad))
         n = max(1, int(req.chunk_count))
-        proofs = [pb.ChunkProof(chunk_id=i, proof_key="%s-%d" % (req.task_id, i),
-                                proof=_h("chunk", req.batch_id, req.batch_data, i).hex()) for i in range(n)]
+        strings = self._chunk_proof_strings(req.batch_id, req.batch_data, n)
+        proofs = [pb.ChunkProof(chunk_id=i, proof_key="%s-%d" % (req.task_id, i), proof=strings[i]) for i in range(n)]
         res = pb.GenChunkProofResult(batch_id=req.batch_id, task_id=req.task_id, result_code=pb.COMPLETED_OK,
                                      batch_proof_result=pb.BatchProofResult(task_id=req.task_id, chunk_proofs=proofs))
         return pb.GenBatchProofResponse(gen_chunk_proof=res)
+
+    @staticmethod
+    def _chunk_proof_strings(batch_id, batch_data, n):
+        return [_h("chunk", batch_id, batch_data, i).hex() for i in range(n)]
+
+    @staticmethod
+    def _aggregated(strings):
+        """what GenAggregatedProof answers when the client sends the first and last chunk proof
+        (provider.rs:386-387, :422-433)"""
+        return _h("agg", strings[0], strings[-1]).hex()
+
+    def _prefetch(self, recursive_proof):
+        """start building the witness of the final circuit for `recursive_proof`, with the aggregator
+        address this operator used last (a constant of the operator, commands/run.rs:76)"""
+        pre = getattr(self.backend, "prefetch", None)
+        if pre is not None and self.last_aggregator is not None:
+            try:
+                pre(recursive_proof, self.last_aggregator)
+            except Exception:
+                log.exception("witness prefetch failed (the final step will generate it)")
 
     def _gen_aggregated(self, req):
         self.ledger.record(req.batch_id, "aggregated")
         result = _h("agg", req.recursive_proof_1, req.recursive_proof_2).hex()
         # the client sends `result` back as GenFinalProofRequest.recursive_proof after its 1 s step
-        # sleep (provider.rs:472-483, :542): start building that witness now, with the aggregator
-        # address this operator used last (it is a constant of the operator, commands/run.rs:76)
-        pre = getattr(self.backend, "prefetch", None)
-        if pre is not None and self.last_aggregator is not None:
-            try:
-                pre(result, self.last_aggregator)
-            except Exception:
-                log.exception("witness prefetch failed (the final step will generate it)")
+        # sleep (provider.rs:472-483, :542); normally this witness was already started at the chunk
+        # step (no-op then), a client that aggregates other proofs gets it started here
+        self._prefetch(result)
         return pb.GenAggregatedProofResponse(batch_id=req.batch_id, result_code=pb.COMPLETED_OK, result_string=result)
 
     # ---- the Groth16 step

@@ -55,6 +55,9 @@ void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
 /* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1),
  * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys),
+ * "assemble_on_device" (0/1, see zkb_groth16_assemble_host),
+ * "msm_sort" (process-wide, default 0 = the library's own bucket sort fused with digit extraction;
+ * 1 = digits kernel + cub::DeviceRadixSort, kept as the comparison baseline),
  * "msm_g2_pair" (process-wide, default 0; 1 = the G2 bucket walk splits each Fq2 point operation
  * over a lane pair — measured slower than one thread per point on B200, kept for comparison) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
@@ -268,6 +271,13 @@ int zkb_pk_synthetic_dist(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, zkb_pk** 
 int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, const uint8_t r[32],
                            const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES],
                            zkb_prove_timings* timings_opt);
+/* The O(1) last step on the host, no context needed: five MSM sums + the key's fixed points + (r, s)
+ * -> proof.  fixed = alpha_g1 64 | beta_g1 64 | delta_g1 64 | beta_g2 128 | delta_g2 128 (canonical).
+ * This is what zkb_groth16_prove / _prove_dist / _assemble run after the MSM phase (the six 254-step
+ * ladders are strictly serial: a CPU core finishes one in 0.15 ms, a lone GPU lane needs 1-3 ms;
+ * ctx tunable "assemble_on_device" = 1 selects the one-CTA device kernel instead, for comparison). */
+int zkb_groth16_assemble_host(const uint8_t fixed[448], const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
+                              const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZKB_PROOF_BYTES]);
 /* CPU pairing check e(A,B) = e(alpha,beta) e(ic0 + x*ic1, gamma) e(C,delta); 0 = valid,
  * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
 int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],
@@ -292,6 +302,9 @@ int zkb_proof_check(const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t public_i
 /* test hook: the decomposed final exponentiation of the verifier against plain square-and-multiply on
  * Miller values built from the proof's points; ZKB_OK when they agree */
 int zkb_selftest_final_exp(const uint8_t proof[ZKB_PROOF_BYTES]);
+/* test hook: proof assembly through the per-key fixed-base tables == through plain ladders */
+int zkb_selftest_assemble_tables(const uint8_t fixed[448], const uint8_t sums[ZKB_INTERMEDIATE_BYTES],
+                                 const uint8_t r[32], const uint8_t s[32]);
 
 /* ---- circuit files -------------------------------------------------------------
  * Readers for the iden3 binary formats circom / snarkjs write (.r1cs constraint systems, .wtns

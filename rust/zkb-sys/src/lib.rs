@@ -134,9 +134,11 @@ extern "C" {
     pub fn zkb_groth16_assemble(ctx: *mut zkb_ctx, pk: *const zkb_pk, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
     pub fn zkb_pk_synthetic_dist(ctx: *mut zkb_ctx, log_n: u32, seed: u64, out_: *mut *mut zkb_pk, vk_out: *mut u8) -> c_int;
     pub fn zkb_groth16_prove_dist(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8, timings_opt: *mut zkb_prove_timings) -> c_int;
+    pub fn zkb_groth16_assemble_host(fixed: *const u8, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
     pub fn zkb_groth16_verify(vk: *const u8, proof: *const u8, public_input: *const u8) -> c_int;
     pub fn zkb_proof_check(proof: *const u8, public_input: *const u8, reasons_opt: *mut u32) -> c_int;
     pub fn zkb_selftest_final_exp(proof: *const u8) -> c_int;
+    pub fn zkb_selftest_assemble_tables(fixed: *const u8, sums: *const u8, r: *const u8, s: *const u8) -> c_int;
     pub fn zkb_r1cs_inspect(file: *const u8, len: u64, out_: *mut zkb_r1cs_info) -> c_int;
     pub fn zkb_r1cs_read(file: *const u8, len: u64, row_ptr: *mut *mut u32, col: *mut *mut u32, coeff: *mut *mut u8) -> c_int;
     pub fn zkb_wtns_inspect(file: *const u8, len: u64, n_witness_out: *mut u32) -> c_int;

@@ -315,3 +315,28 @@ def test_fast_final_exponentiation_equals_square_and_multiply(zkb):
     with pytest.raises(zkb.ZkbError):
         zkb.groth16_verify(bytes(bad_vk), proof, wit[32:64])
     assert zkb.groth16_verify(opk.vk(), proof, wit[32:64])
+
+
+def test_host_proof_assembly_matches_oracle(zkb):
+    """K15 on the host: the six scalar multiplications and additions that turn the five MSM sums into
+    (A, B, C) — against oracle B's proof bytes for full-size and edge blinding scalars."""
+    import time
+    log_n, seed = 6, 404
+    opk = ob.ProvingKey(log_n, seed)
+    wit = ob.synthetic_witness(log_n, fr_bytes([12]), fr_bytes([34]))
+    rng = o.Xoshiro256ss(9)
+    cases = [(rng.fr(), rng.fr()), (0, 0), (1, o.R - 1), (o.R - 1, 1), (5, 0)]
+    for r, s in cases:
+        rb, sb = fr_bytes([r]), fr_bytes([s])
+        proof, inter, _, _ = opk.prove(wit, rb, sb)
+        t0 = time.perf_counter()
+        got = zkb.lib.groth16_assemble_host(opk.fixed(), inter, rb, sb)
+        dt = time.perf_counter() - t0
+        assert got == proof, (r, s)
+        assert zkb.groth16_verify(opk.vk(), got, wit[32:64])
+        f = opk.fixed()
+        blob = f["alpha_g1"] + f["beta_g1"] + f["delta_g1"] + f["beta_g2"] + f["delta_g2"]
+        assert zkb.load_library().zkb_selftest_assemble_tables(blob, inter, rb, sb) == 0, (r, s)
+    assert dt < 0.05
+    with pytest.raises(zkb.ZkbError):
+        zkb.lib.groth16_assemble_host(opk.fixed(), inter, fr_bytes([1]), int(o.R).to_bytes(32, "little"))

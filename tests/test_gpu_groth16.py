@@ -43,6 +43,14 @@ def test_prove_bit_exact_vs_oracle(ctx, zkb, log_n):
     # different blinding -> different but still valid proof
     proof3, _, _, _ = ctx.groth16_prove(pk, wit, s, r)
     assert proof3 != proof and zkb.groth16_verify(pk.vk, proof3, wit[32:64])
+    # the final assembly runs on the host by default (six serial 254-step ladders); the one-CTA device
+    # kernel is the comparison path and must give the same bytes
+    ctx.set("assemble_on_device", 1)
+    try:
+        proof4, _, _, _ = ctx.groth16_prove(pk, wit, r, s)
+    finally:
+        ctx.set("assemble_on_device", 0)
+    assert proof4 == proof
     pk.free()
     opk.free()
 

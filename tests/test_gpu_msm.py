@@ -269,3 +269,38 @@ def test_g2_msm_closed_form_2p20(ctx):
     bases.precompute(0)
     assert ctx.msm(bases, sc) == want
     bases.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_both_sort_implementations_agree(ctx, mode):
+    """msm_sort = 0: the library's own bucket sort fused with the digit extraction (default);
+    msm_sort = 1: digits kernel + cub::DeviceRadixSort (comparison baseline).  Same results on uniform,
+    0/1, all-equal (every entry in a handful of buckets -> the multi-segment path of the bucket sort)
+    and r - 1 scalars, classic and precomputed bases, G1 and G2."""
+    import oracle_b as ob
+    ctx.set("msm_sort", mode)
+    try:
+        rng = o.Xoshiro256ss(8800)
+        pts = _g1_points(rng, 257)
+        pts[9] = None
+        sc = rand_fr(rng, 257)
+        bases = ctx.upload_bases(g1_bytes(pts))
+        for w in (0, 4, 11, 16):
+            ctx.set("msm_window", w)
+            assert o.g1_from_bytes(ctx.msm(bases, fr_bytes(sc))) == o.msm_g1(pts, sc), w
+        ctx.set("msm_window", 0)
+        n, seed = 1 << 18, 0x5EED0123
+        big = ctx.synthetic_bases(n, seed)
+        cases = {"uniform": ob.random_scalars(n, 5), "bits": b"".join(((i * 3) & 1).to_bytes(32, "little") for i in range(n)),
+                 "same": (0xABCDEF << 180 | 77).to_bytes(32, "little") * n, "r-1": int(o.R - 1).to_bytes(32, "little") * n}
+        for precomp in (False, True):
+            if precomp:
+                big.precompute(0)
+            for name, s in cases.items():
+                assert ctx.msm(big, s) == ob.msm_closed_form(s, n, seed), (name, precomp)
+        g2 = ctx.synthetic_bases(1 << 12, seed + 1, g2=True)
+        s = ob.random_scalars(1 << 12, 6)
+        assert ctx.msm(g2, s) == ob.msm_closed_form(s, 1 << 12, seed + 1, g2=True)
+    finally:
+        ctx.set("msm_sort", 0)
+        ctx.set("msm_window", 0)

@@ -248,8 +248,10 @@ def test_aggregate_step_prefetches_the_final_witness(server):
     seen = []
     backend.prefetch = lambda rp, agg: seen.append((rp, agg))
     op = OperatorReplay(addr, step_sleep=0.0)
-    op.execute(5, batch_id="pf-1")
+    res, _ = op.execute(5, batch_id="pf-1")
     op.close()
-    assert len(seen) == 1
+    # started at the chunk step already (three client sleeps ahead of GenFinalProof), confirmed at the
+    # aggregate step: both name the very string the client later sends as recursive_proof
+    assert len(seen) == 2 and seen[0] == seen[1]
     rp, agg = seen[0]
     assert agg == op.aggregator and len(rp) == 64
