@@ -907,7 +907,7 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
     return ZKB_OK;
   }
   if (!std::strcmp(key, "msm_g2_pair")) {     // process-wide comparison switch, see msm_g2.cu
-    msm_set_g2_pair(value ? 1 : 0);
+    msm_set_g2_pair(int(value) & 3);
     return ZKB_OK;
   }
   if (!std::strcmp(key, "msm_profile")) {

@@ -21,7 +21,7 @@ struct MsmPlan {
   uint64_t n_buckets;       // n_sets * half (also the sentinel key of zero digits)
   uint64_t m;               // n * nwin (key, value) pairs
   int key_bits;             // radix-sort key width
-  int g2_pair;              // G2 only: level-1 walk splits one Fq2 point operation over a lane pair
+  int g2_pair;              // G2 only: bit 0 lane-pair walk, bit 1 lane-pair tail kernels
   int sort_mode;            // 0 = hand-written bucket sort, 1 = cub radix sort
   int sm_count;
   uint32_t l1_threads;      // chunks of the level-1 walk
@@ -65,7 +65,8 @@ int msm_auto_window(uint64_t n, bool precomputed);
 // resident threads per SM the level-1 walk kernel of each curve is compiled for (launch bounds)
 uint32_t msm_l1_threads_per_sm_g1();
 uint32_t msm_l1_threads_per_sm_g2(int pair);
-// process-wide comparison switch (zkb_ctx_set "msm_g2_pair"): 1 = lane-pair G2 walk; default 0
+// process-wide comparison switch (zkb_ctx_set "msm_g2_pair"): bit 0 = lane-pair G2 walk, bit 1 = lane-pair
+// latency-bound G2 kernels (default 2)
 void msm_set_g2_pair(int on);
 int msm_get_g2_pair();
 // out[w * n + i] = 2^{c w} * in[i], w < nwin (affine Montgomery in and out; in may alias out[0..n))

@@ -13,11 +13,11 @@ namespace zkb {
 static std::atomic<uint64_t> g_launches{0};
 void count_launches(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
-static std::atomic<int> g_g2_pair{0};   // measured on B200: the lane-pair walk is 5 % slower
+static std::atomic<int> g_g2_pair{2};   // bit 0: lane-pair walk (5 % slower on B200), bit 1: lane-pair tails
 static std::atomic<int> g_sort_mode{0};
 void msm_set_sort_mode(int mode) { g_sort_mode.store(mode ? 1 : 0); }
 int msm_get_sort_mode() { return g_sort_mode.load(); }
-void msm_set_g2_pair(int on) { g_g2_pair.store(on ? 1 : 0); }
+void msm_set_g2_pair(int on) { g_g2_pair.store(on & 3); }
 int msm_get_g2_pair() { return g_g2_pair.load(); }
 
 // ---------------------------------------------------------------- 1. digits

@@ -1,6 +1,13 @@
 // msm_g2.cu — BN254 G2 instantiation of the MSM pipeline (coordinates in Fq2 on the twist).
-// The bucket walk runs on Fq2 (every product inlined); the latency-bound kernels around it run on
-// Fq2C, the same field with out-of-line products (ff.cuh) — same memory layout.
+// Three register-level forms of the same field, one memory layout (ff.cuh):
+//   Fq2   every product inlined          -> the bucket walk (throughput-bound, best pipe use)
+//   Fq2L  one element over a lane pair   -> the latency-bound kernels around the walk (partial merges,
+//                                           bucket reduction, window sums, Horner): half the dependent
+//                                           IMAD.WIDE chain per lane, twice the warps on idle SMs
+//   Fq2C  out-of-line products           -> the same kernels without lane pairing (comparison), and
+//                                           the setup kernels (small code)
+// Process-wide comparison switch "msm_g2_pair": bit 0 = lane-pair WALK (measured 5 % slower than the
+// one-thread walk), bit 1 = lane-pair latency-bound kernels (default).
 #include "msm_impl.cuh"
 
 namespace zkb {
@@ -8,15 +15,19 @@ template <> struct L1Cfg<Fq2C> { static constexpr int kMinBlocks = 2; };
 
 void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
                        cudaStream_t s) {
-  // level-1 walk: one thread per point (8 warps / SM, 255 registers), or — comparison switch — one Fq2
-  // point operation split over a lane pair (Fq2L, 16 warps / SM; 5 % slower on B200)
-  if (p.g2_pair) msm_accumulate_t<Fq2C, Fq2L>(p, b, d_bases, bucket_target, s);
-  else msm_accumulate_t<Fq2C, Fq2>(p, b, d_bases, bucket_target, s);
+  const bool pair_walk = p.g2_pair & 1, pair_tail = p.g2_pair & 2;
+  if (pair_walk && pair_tail) msm_accumulate_t<Fq2, Fq2L, Fq2L>(p, b, d_bases, bucket_target, s);
+  else if (pair_walk) msm_accumulate_t<Fq2, Fq2L, Fq2C>(p, b, d_bases, bucket_target, s);
+  else if (pair_tail) msm_accumulate_t<Fq2, Fq2, Fq2L>(p, b, d_bases, bucket_target, s);
+  else msm_accumulate_t<Fq2, Fq2, Fq2C>(p, b, d_bases, bucket_target, s);
 }
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
   msm_merge_t<Fq2C>(p, main_buckets, part_buckets, s);
 }
-void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) { msm_tail_t<Fq2C>(p, b, s); }
+void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
+  if (p.g2_pair & 2) msm_tail_t<Fq2L>(p, b, s);
+  else msm_tail_t<Fq2C>(p, b, s);
+}
 void msm_bases_to_mont_g2(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {
   msm_bases_to_mont_t<Fq2>(d_pts, n, b_mont, d_flag, s);
 }
@@ -28,6 +39,6 @@ void msm_precompute_g2(const void* d_in, void* d_out, uint64_t n, uint32_t nwin,
 }
 // chunks (not threads) walked concurrently per SM
 uint32_t msm_l1_threads_per_sm_g2(int pair) {
-  return pair ? 128u * L1Cfg<Fq2L>::kMinBlocks / Fq2L::kLanes : 128u * L1Cfg<Fq2>::kMinBlocks;
+  return (pair & 1) ? 128u * L1Cfg<Fq2L>::kMinBlocks / Fq2L::kLanes : 128u * L1Cfg<Fq2>::kMinBlocks;
 }
 }  // namespace zkb

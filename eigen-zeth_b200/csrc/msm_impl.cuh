@@ -95,14 +95,25 @@ __global__ void __launch_bounds__(128, L1Cfg<F>::kMinBlocks) msm_accumulate_l1_k
   }
 }
 
+// The kernels below (partial merges, bucket reduction, window sums, Horner) are short chains of
+// dependent point additions on small grids: latency-bound.  They address memory in bytes and let
+// F::kLanes adjacent lanes share one work item, so G2 can run them on Fq2L (one Fq2 operation over a
+// lane pair: half the dependent IMAD.WIDE chain per lane, twice the warps on otherwise idle SMs).
+template <class F> __device__ __forceinline__ XYZZ<F> ld_pt(const char* base, uint64_t idx) {
+  return XYZZ<F>::load(base + idx * (4 * size_t(F::kBytes)));
+}
+template <class F> __device__ __forceinline__ void st_pt(const XYZZ<F>& v, char* base, uint64_t idx) {
+  v.store(base + idx * (4 * size_t(F::kBytes)));
+}
+
 // ---------------------------------------------------------------- 4. accumulate, level 2
 // Same walk over a (key, XYZZ) list that may contain kInvalidKey holes.
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate_l2_kernel(
-    const uint32_t* __restrict__ keys, const XYZZ<F>* __restrict__ pts, uint32_t m, uint32_t len,
-    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ part_keys,
-    XYZZ<F>* __restrict__ part_pts, uint32_t n_threads) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* __restrict__ keys, const char* __restrict__ pts, uint32_t m, uint32_t len,
+    char* __restrict__ buckets, uint32_t* __restrict__ part_keys,
+    char* __restrict__ part_pts, uint32_t n_threads) {
+  uint32_t tid = (blockIdx.x * blockDim.x + threadIdx.x) / F::kLanes;
   if (tid >= n_threads) return;
   uint32_t start = tid * len;
   uint32_t end = start + len < m ? start + len : m;
@@ -118,33 +129,33 @@ __global__ void __launch_bounds__(128) msm_accumulate_l2_kernel(
     if (key != cur) {
       if (first_run) {
         part_keys[2 * tid] = cur;
-        acc.store(part_pts + 2 * tid);
+        st_pt<F>(acc, part_pts, 2 * tid);
         first_run = false;
       } else {
-        acc.store(buckets + cur);
+        st_pt<F>(acc, buckets, cur);
       }
       acc = XYZZ<F>::infinity();
       cur = key;
     }
-    acc.add(XYZZ<F>::load(pts + i));
+    acc.add(ld_pt<F>(pts, i));
   }
   if (cur == kInvalidKey) return;
   if (first_run) {
     part_keys[2 * tid] = cur;
-    acc.store(part_pts + 2 * tid);
+    st_pt<F>(acc, part_pts, 2 * tid);
   } else {
     part_keys[2 * tid + 1] = cur;
-    acc.store(part_pts + 2 * tid + 1);
+    st_pt<F>(acc, part_pts, 2 * tid + 1);
   }
 }
 
 // ---------------------------------------------------------------- 5. finish
-// One thread per list entry; the thread that holds the first valid entry of a key sums the run.
+// One work item per list entry; the item that holds the first valid entry of a key sums the run.
 template <class F>
 __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restrict__ keys,
-                                                         const XYZZ<F>* __restrict__ pts,
-                                                         uint32_t m, XYZZ<F>* __restrict__ buckets) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                         const char* __restrict__ pts,
+                                                         uint32_t m, char* __restrict__ buckets) {
+  uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / F::kLanes;
   if (i >= m) return;
   uint32_t key = keys[i];
   if (key == kInvalidKey) return;
@@ -154,20 +165,20 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restr
     if (kp == key) return;
     break;
   }
-  XYZZ<F> acc = XYZZ<F>::load(pts + i);
+  XYZZ<F> acc = ld_pt<F>(pts, i);
   for (uint32_t j = i + 1; j < m; j++) {
     uint32_t kn = keys[j];
     if (kn == kInvalidKey) continue;
     if (kn != key) break;
-    acc.add(XYZZ<F>::load(pts + j));
+    acc.add(ld_pt<F>(pts, j));
   }
-  acc.store(buckets + key);
+  st_pt<F>(acc, buckets, key);
 }
 
 // ---------------------------------------------------------------- 6. bucket reduce
 // sum_j (j+1) B_j without any scalar multiplication: with zero-based weights W0(B) = sum_j j B_j
 // and groups of 16,  W0(B) = sum_g w0_g + 16 * W0(run),  w0_g = sum_t t B_{16g+t},
-// run_g = sum_t B_{16g+t}.  One level = one launch: thread g turns 16 inputs into (run_g, w0_g)
+// run_g = sum_t B_{16g+t}.  One level = one launch: item g turns 16 inputs into (run_g, w0_g)
 // with 31 additions; the runs are the next level's input (16x fewer), the w0's of a level are
 // summed by the window-sum kernel, and the answer is  S + sum_l 16^l W_l  (S = sum of the runs of
 // the last level).  Each level is a latency-bound launch, so only arrays of >= 2^20 buckets take a
@@ -175,61 +186,62 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restr
 constexpr uint32_t kRedGroup = 16;
 
 template <class F>
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const XYZZ<F>* __restrict__ in,
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const char* __restrict__ in,
                                                                uint32_t count, uint32_t groups,
-                                                               uint32_t n_sets, XYZZ<F>* __restrict__ run_out,
-                                                               XYZZ<F>* __restrict__ w0_out, int last_level) {
-  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+                                                               uint32_t n_sets, char* __restrict__ run_out,
+                                                               char* __restrict__ w0_out, int last_level) {
+  uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / F::kLanes;
   if (gid >= groups * n_sets) return;
   uint32_t set = gid / groups, g = gid - set * groups;
-  const XYZZ<F>* b = in + uint64_t(set) * count + uint64_t(g) * kRedGroup;
+  const uint64_t b = uint64_t(set) * count + uint64_t(g) * kRedGroup;
   uint32_t avail = count - g * kRedGroup;
   if (avail > kRedGroup) avail = kRedGroup;
   XYZZ<F> r = XYZZ<F>::infinity(), w = XYZZ<F>::infinity();
   for (int t = int(avail) - 1; t >= 1; t--) {
-    r.add(XYZZ<F>::load(b + t));
+    r.add(ld_pt<F>(in, b + t));
     w.add(r);
   }
-  r.add(XYZZ<F>::load(b));
+  r.add(ld_pt<F>(in, b));
   // the last level closes the recursion with one small scalar multiplication per group:
   // sum_j j x_j over the whole array = sum_g (w0_g + 16 g run_g)
   if (last_level && g) w.add(mul_small(r, g * kRedGroup));
-  r.store(run_out + gid);
-  w.store(w0_out + gid);
+  st_pt<F>(r, run_out, gid);
+  st_pt<F>(w, w0_out, gid);
 }
 
 // ---------------------------------------------------------------- 7. window sum
-// CTA (set, slice) sums its slice of the `count` points of a set (serial per thread, then a shared
-// memory tree).  Launched twice: group sums -> `slices` partials per set -> one point per set.
+// CTA (set, slice) sums its slice of the `count` points of a set (serial per item, then a shared
+// memory tree over the blockDim.x / kLanes items).  Launched twice: group sums -> `slices` partials
+// per set -> one point per set.
 template <class F>
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const XYZZ<F>* __restrict__ in,
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const char* __restrict__ in,
                                                              uint32_t count, uint32_t slices,
-                                                             XYZZ<F>* __restrict__ out) {
+                                                             char* __restrict__ out) {
   extern __shared__ uint4 sm_raw[];
-  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sm_raw);
-  const uint32_t set = blockIdx.x / slices, slice = blockIdx.x - set * slices, t = threadIdx.x;
+  char* sm = reinterpret_cast<char*>(sm_raw);
+  const uint32_t items = blockDim.x / F::kLanes;
+  const uint32_t set = blockIdx.x / slices, slice = blockIdx.x - set * slices, t = threadIdx.x / F::kLanes;
   const uint32_t len = (count + slices - 1) / slices;
   const uint32_t lo = slice * len, hi = lo + len < count ? lo + len : count;
   XYZZ<F> acc = XYZZ<F>::infinity();
-  for (uint32_t g = lo + t; g < hi; g += blockDim.x)
-    acc.add(XYZZ<F>::load(in + uint64_t(set) * count + g));
-  acc.store(sm + t);
+  for (uint32_t g = lo + t; g < hi; g += items) acc.add(ld_pt<F>(in, uint64_t(set) * count + g));
+  st_pt<F>(acc, sm, t);
   __syncthreads();
-  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+  for (uint32_t s = items >> 1; s > 0; s >>= 1) {
     if (t < s) {
-      XYZZ<F> a = XYZZ<F>::load(sm + t);
-      a.add(XYZZ<F>::load(sm + t + s));
-      a.store(sm + t);
+      XYZZ<F> a = ld_pt<F>(sm, t);
+      a.add(ld_pt<F>(sm, t + s));
+      st_pt<F>(a, sm, t);
     }
     __syncthreads();
   }
-  if (t == 0) XYZZ<F>::load(sm).store(out + blockIdx.x);
+  if (t == 0) st_pt<F>(ld_pt<F>(sm, 0), out, blockIdx.x);
 }
 
 // ---------------------------------------------------------------- 8. Horner + output
 // per set: S + sum_l 16^l W_l (Horner over the reduce levels, 4 doublings each), then Horner over
 // the sets with c doublings each.  wl is [level][set]; s_tot is [set].
-// result (Montgomery XYZZ, 4*sizeof(F) bytes) and canonical affine (2*sizeof(F) bytes)
+// result (Montgomery XYZZ, 4*F::kBytes bytes) and canonical affine (2*F::kBytes bytes)
 // Independent mode (outs.n != 0): the sets are the bucket sets of DIFFERENT MSMs (one each, bases with
 // precomputed window multiples) reduced by one shared tail; set t writes its own canonical affine
 // result to outs.p[t] and nothing is combined across sets.
@@ -239,35 +251,35 @@ struct MsmOutPtrs {
 };
 
 template <class F>
-__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ wl, const XYZZ<F>* __restrict__ s_tot,
+__global__ void msm_horner_kernel(const char* __restrict__ wl, const char* __restrict__ s_tot,
                                   uint32_t levels, uint32_t n_sets, uint32_t c,
-                                  XYZZ<F>* __restrict__ set_sums, XYZZ<F>* __restrict__ out_xyzz,
-                                  Affine<F>* __restrict__ out_affine, MsmOutPtrs outs) {
-  const uint32_t t = threadIdx.x;
+                                  char* __restrict__ set_sums, char* __restrict__ out_xyzz,
+                                  char* __restrict__ out_affine, MsmOutPtrs outs) {
+  const uint32_t t = threadIdx.x / F::kLanes;
   if (blockIdx.x) return;
   if (t < n_sets) {
-    XYZZ<F> acc = XYZZ<F>::load(wl + uint64_t(levels - 1) * n_sets + t);
+    XYZZ<F> acc = ld_pt<F>(wl, uint64_t(levels - 1) * n_sets + t);
     for (int l = int(levels) - 2; l >= 0; l--) {
       for (int k = 0; k < 4; k++) acc = acc.dbl();
-      acc.add(XYZZ<F>::load(wl + uint64_t(l) * n_sets + t));
+      acc.add(ld_pt<F>(wl, uint64_t(l) * n_sets + t));
     }
-    acc.add(XYZZ<F>::load(s_tot + t));
+    acc.add(ld_pt<F>(s_tot, t));
     if (outs.n) {
       Affine<F> a = acc.to_affine();
       a.x = a.x.from_mont();
       a.y = a.y.from_mont();
       a.store(outs.p[t]);
     } else {
-      acc.store(set_sums + t);
+      st_pt<F>(acc, set_sums, t);
     }
   }
   if (outs.n) return;
   __syncthreads();
   if (t) return;
-  XYZZ<F> acc = XYZZ<F>::load(set_sums + (n_sets - 1));
+  XYZZ<F> acc = ld_pt<F>(set_sums, n_sets - 1);
   for (int w = int(n_sets) - 2; w >= 0; w--) {
     for (uint32_t i = 0; i < c; i++) acc = acc.dbl();
-    acc.add(XYZZ<F>::load(set_sums + w));
+    acc.add(ld_pt<F>(set_sums, w));
   }
   acc.store(out_xyzz);
   Affine<F> a = acc.to_affine();
@@ -325,13 +337,15 @@ __global__ void __launch_bounds__(128) msm_bucket_merge_kernel(XYZZ<F>* __restri
 }
 
 // sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first).
-// FW is the register-level field type of the level-1 walk (F itself, or Fq2L for F = Fq2).
-template <class F, class FW = F>
+// FW is the register-level field type of the level-1 walk, FT that of the latency-bound kernels
+// after it (F itself, or a type with the same storage layout: Fq2C / Fq2L for F = Fq2).
+template <class F, class FW = F, class FT = F>
 void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases,
                       void* bucket_target, cudaStream_t s) {
-  using P = XYZZ<F>;
-  static_assert(F::kBytes == FW::kBytes, "walk type must share the storage layout");
-  cudaMemsetAsync(bucket_target, 0, p.n_buckets * sizeof(P), s);
+  static_assert(F::kBytes == FW::kBytes && F::kBytes == FT::kBytes, "walk types must share the storage layout");
+  constexpr size_t kPt = 4 * size_t(F::kBytes);
+  constexpr uint32_t L = FT::kLanes;
+  cudaMemsetAsync(bucket_target, 0, p.n_buckets * kPt, s);
   msm_accumulate_l1_kernel<FW><<<(p.l1_threads * FW::kLanes + 127) / 128, 128, 0, s>>>(
       b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const char*>(d_bases),
       reinterpret_cast<char*>(bucket_target), b.part1_keys, reinterpret_cast<char*>(b.part1_pts),
@@ -344,20 +358,20 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
   // costs a few short passes, never a long serial chain.
   uint32_t* keys_a = b.part1_keys;
   uint32_t* keys_b = b.part2_keys;
-  P* pts_a = reinterpret_cast<P*>(b.part1_pts);
-  P* pts_b = reinterpret_cast<P*>(b.part2_pts);
+  char* pts_a = reinterpret_cast<char*>(b.part1_pts);
+  char* pts_b = reinterpret_cast<char*>(b.part2_pts);
   uint32_t count = 2 * p.l1_threads;
   do {
     uint32_t threads = (count + p.l2_len - 1) / p.l2_len;
-    msm_accumulate_l2_kernel<F><<<(threads + 127) / 128, 128, 0, s>>>(
-        keys_a, pts_a, count, p.l2_len, reinterpret_cast<P*>(bucket_target), keys_b, pts_b, threads);
+    msm_accumulate_l2_kernel<FT><<<(threads * L + 127) / 128, 128, 0, s>>>(
+        keys_a, pts_a, count, p.l2_len, reinterpret_cast<char*>(bucket_target), keys_b, pts_b, threads);
     count_launches(1);
     count = 2 * threads;
     uint32_t* tk = keys_a; keys_a = keys_b; keys_b = tk;
-    P* tp = pts_a; pts_a = pts_b; pts_b = tp;
+    char* tp = pts_a; pts_a = pts_b; pts_b = tp;
   } while (count > 1024);
-  msm_finish_kernel<F><<<(count + 127) / 128, 128, 0, s>>>(keys_a, pts_a, count,
-                                                           reinterpret_cast<P*>(bucket_target));
+  msm_finish_kernel<FT><<<(count * L + 127) / 128, 128, 0, s>>>(keys_a, pts_a, count,
+                                                               reinterpret_cast<char*>(bucket_target));
   count_launches(1);
   if (b.ev) cudaEventRecord(b.ev[4], s);
 }
@@ -375,46 +389,46 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
 // b.window_sums: [levels][n_sets] W_l, [n_sets] S, [n_sets] set sums
 template <class F>
 void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const MsmOutPtrs* independent = nullptr) {
-  using P = XYZZ<F>;
-  P* scratch = reinterpret_cast<P*>(b.group_sums);
-  P* wl = reinterpret_cast<P*>(b.window_sums);
-  const P* in = reinterpret_cast<const P*>(b.buckets);
+  constexpr size_t kPt = 4 * size_t(F::kBytes);
+  constexpr uint32_t L = F::kLanes;
+  char* scratch = reinterpret_cast<char*>(b.group_sums);
+  char* wl = reinterpret_cast<char*>(b.window_sums);
+  const char* in = reinterpret_cast<const char*>(b.buckets);
   uint32_t count = p.half;
-  P* run_cursor = scratch;
-  P* w0 = scratch + p.red_run_total;
-  P* stage = w0 + uint64_t(p.n_sets) * ((p.half + kRedGroup - 1) / kRedGroup);
+  char* run_cursor = scratch;
+  char* w0 = scratch + p.red_run_total * kPt;
+  char* stage = w0 + uint64_t(p.n_sets) * ((p.half + kRedGroup - 1) / kRedGroup) * kPt;
+  const size_t smem = (128 / L) * kPt;
   uint32_t groups = 0;
   for (uint32_t l = 0; l < p.red_levels; l++) {
     groups = (count + kRedGroup - 1) / kRedGroup;
     uint32_t threads = groups * p.n_sets;
     const int last = l + 1 == p.red_levels;
-    msm_reduce_level_kernel<F><<<(threads + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
+    msm_reduce_level_kernel<F><<<(threads * L + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
     // W_l[set] = sum of this level's w0 (two-stage when there are many)
     const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
-    P* wl_out = wl + uint64_t(l) * p.n_sets;
-    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(w0, groups, slices,
-                                                                             slices > 1 ? stage : wl_out);
-    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, wl_out);
+    char* wl_out = wl + uint64_t(l) * p.n_sets * kPt;
+    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, smem, s>>>(w0, groups, slices, slices > 1 ? stage : wl_out);
+    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, smem, s>>>(stage, slices, 1, wl_out);
     count_launches(slices > 1 ? 3 : 2);
     in = run_cursor;
-    run_cursor += uint64_t(threads);
+    run_cursor += uint64_t(threads) * kPt;
     count = groups;
   }
   // S[set] = sum of the runs of the last level
-  P* s_tot = wl + uint64_t(p.red_levels) * p.n_sets;
+  char* s_tot = wl + uint64_t(p.red_levels) * p.n_sets * kPt;
   {
     const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
-    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, 128 * sizeof(P), s>>>(in, groups, slices,
-                                                                             slices > 1 ? stage : s_tot);
-    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, 128 * sizeof(P), s>>>(stage, slices, 1, s_tot);
+    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, smem, s>>>(in, groups, slices, slices > 1 ? stage : s_tot);
+    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, smem, s>>>(stage, slices, 1, s_tot);
     count_launches(slices > 1 ? 3 : 2);   // + the Horner kernel below
   }
   MsmOutPtrs outs{};
   if (independent) outs = *independent;
-  msm_horner_kernel<F><<<1, 128, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,
-                                         wl + uint64_t(p.red_levels + 1) * p.n_sets,
-                                         reinterpret_cast<P*>(b.result_xyzz),
-                                         reinterpret_cast<Affine<F>*>(b.result_affine), outs);
+  msm_horner_kernel<F><<<1, 128 * L, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,
+                                         wl + uint64_t(p.red_levels + 1) * p.n_sets * kPt,
+                                         reinterpret_cast<char*>(b.result_xyzz),
+                                         reinterpret_cast<char*>(b.result_affine), outs);
   if (b.ev) cudaEventRecord(b.ev[5], s);
 }
 

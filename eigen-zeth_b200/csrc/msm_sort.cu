@@ -6,26 +6,30 @@
 // entry in HBM -> a generic 3-pass LSD radix sort:
 //
 //   A  histogram   read the scalars, recompute every signed digit, count entries per COARSE bin
-//                  (key >> lo_bits) in shared memory, one global atomic per (tile, bin).
+//                  (key >> lo_bits, at most 2^11 bins) in shared memory, one global atomic per (tile, bin).
 //   P  plan        one CTA: exclusive scan of the coarse histogram (= where each bin starts in the
 //                  output AND in the intermediate array), m_valid, and the work list of pass C:
 //                  one item per bin, or several per bin when a bin is larger than a CTA can hold.
-//   B  scatter     read the scalars again (L2), recompute the digits, reserve room per (tile, bin)
-//                  with one global atomic, write (key, value) into the bin's region.  Every bin has
-//                  ONE moving write frontier, so the set of partially written lines is H x 128 B —
-//                  far below the 126 MB L2, which merges the short runs before they reach HBM.
+//   B  scatter     a tile = the <= kCap entries of ~kCap / windows scalars.  The tile is counting-sorted
+//                  by coarse bin INSIDE shared memory (count, scan, place), room is reserved per
+//                  (tile, bin) with one global atomic, and the staged tile is written out linearly:
+//                  neighbouring threads write neighbouring entries of one run (~10 entries = 80 B per
+//                  bin per tile with 2^11 bins), so the stores coalesce and every run is written at
+//                  once.  (A first version scattered straight from registers: each of the ~450
+//                  resident tiles then kept 16 K half-written lines open, 900 MB of them — far beyond
+//                  the 126 MB L2 — and the pass took 7 ms at 2^24 points instead of < 1 ms.)
 //   C  bucketize   one CTA per work item loads its segment (<= kCap entries, 8 B each) into shared
-//                  memory, counts the fine buckets (key & (2^lo_bits - 1)), scans, and writes every
-//                  entry to its final position; a whole bin is one CTA's private output region, so
-//                  its scattered 4-byte writes also complete whole lines inside L2.
-//                  Oversized bins (skewed scalars: 0/1 witnesses, all-equal scalars) are cut into
-//                  segments that first add their fine histograms into a global table (C1), get their
-//                  bucket offsets from a per-bin scan (C1s) and reserve output ranges with global
-//                  atomics (C2) — same result, any distribution.
+//                  memory, counting-sorts it by fine bucket (key & (2^lo_bits - 1)) in shared memory
+//                  and writes it out linearly to the bucket's final position.  A bin that fits one
+//                  segment is the CTA's private output region (offsets from a local scan).  Larger
+//                  bins — the rule at 2^24 points, and any skewed input (0/1 witnesses, all-equal
+//                  scalars) — are cut into segments that first add their fine histograms into a global
+//                  table (C1), get bucket offsets from a per-bin scan (C1s) and reserve their output
+//                  runs with global atomics (C2): same result for any distribution.
 // Zero digits are never emitted (no sentinel key, no count kernel).  HBM traffic per entry: 8 B
-// written + 8 B read + 8 B written, plus 2 x 32 B per scalar — against 16 B + 3 x 16 B + histogram
-// for digits + cub::DeviceRadixSort.  The order inside a bucket is not deterministic; the bucket SUM
-// is, and results are compared in canonical affine form.
+// written + 8 B read (+ 8 B read for C1) + 8 B written, plus 2 x 32 B per scalar — against 16 B +
+// 3 x 16 B + histogram for digits + cub::DeviceRadixSort.  The order inside a bucket is not
+// deterministic; the bucket SUM is, and results are compared in canonical affine form.
 #include <cuda_runtime.h>
 
 #include <mutex>
@@ -36,8 +40,8 @@ namespace zkb {
 
 constexpr uint32_t kSortThreads = 512;
 constexpr uint32_t kPlaceThreads = 1024;
-constexpr uint32_t kCap = 20480;            // entries a pass-C CTA holds in shared memory (160 KB)
-constexpr uint32_t kMaxCoarse = 16384;      // coarse bins (64 KB of shared counters in passes A / B)
+constexpr uint32_t kCap = 20480;            // entries a pass-B tile / pass-C segment holds in shared memory (160 KB)
+constexpr uint32_t kMaxCoarse = 2048;       // coarse bins: ~10 entries per (tile, bin) run
 constexpr uint32_t kMaxFine = 4096;         // fine buckets per coarse bin
 
 // signed-digit extraction shared by passes A and B (same recoding as msm_digits_kernel)
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(const uint32_t* __restr
   for (uint32_t b = lo; b < hi; b++) {
     uint32_t v = coarse_hist[b];
     sum += v;
-    segs += (v + kCap - 1) / kCap;
+    segs += (v + kCap / 2 - 1) / (kCap / 2);
   }
   s_sum[t] = sum;
   s_seg[t] = segs;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(const uint32_t* __restr
     uint32_t v = coarse_hist[b];
     coarse_off[b] = off;
     cursor[b] = off;
-    uint32_t ns = (v + kCap - 1) / kCap;
+    uint32_t ns = (v + kCap / 2 - 1) / (kCap / 2);
     bin_multi[b] = ns > 1;
     for (uint32_t s = 0; s < ns; s++) items[item + s] = make_uint2(b, s);
     item += ns;
@@ -153,30 +157,70 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(const uint32_t* __restr
   }
 }
 
+// exclusive scan of v[0..n) in shared memory by the whole CTA (n <= 4 * blockDim.x is typical);
+// `part` is blockDim.x words of scratch.  On return v[i] = sum of the old v[0..i).
+__device__ __forceinline__ void block_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* part) {
+  const uint32_t t = threadIdx.x, T = blockDim.x, per = (n + T - 1) / T;
+  const uint32_t lo = t * per, hi = lo + per < n ? lo + per : n;
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += v[i];
+  part[t] = sum;
+  __syncthreads();
+  for (uint32_t o = 1; o < T; o <<= 1) {
+    uint32_t a = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += a;
+    __syncthreads();
+  }
+  uint32_t off = part[t] - sum;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t c = v[i];
+    v[i] = off;
+    off += c;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------- B: scatter into coarse bins
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
-                                                                    DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
-                                                                    uint32_t per_cta, uint32_t* __restrict__ cursor,
-                                                                    uint2* __restrict__ mid) {
-  extern __shared__ uint32_t sm_cnt[];
-  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) sm_cnt[b] = 0;
+// dynamic shared memory: kCap staged entries | n_coarse run cursors | n_coarse (global base - local start)
+__global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
+                                                                     DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
+                                                                     uint32_t per_cta, uint32_t* __restrict__ cursor,
+                                                                     uint2* __restrict__ mid) {
+  extern __shared__ uint2 sm_stage[];
+  uint32_t* run = reinterpret_cast<uint32_t*>(sm_stage + kCap);
+  uint32_t* gbase = run + n_coarse;
+  __shared__ uint32_t part[kPlaceThreads];
+  __shared__ uint32_t total;
+  const uint32_t t = threadIdx.x;
+  for (uint32_t b = t; b < n_coarse; b += blockDim.x) run[b] = 0;
   __syncthreads();
   const uint64_t first = uint64_t(blockIdx.x) * per_cta;
   const uint64_t last = first + per_cta < n ? first + per_cta : n;
-  for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
-    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t) { atomicAdd(&sm_cnt[key >> lo_bits], 1u); });
+  for (uint64_t i = first + t; i < last; i += blockDim.x)
+    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t) { atomicAdd(&run[key >> lo_bits], 1u); });
   __syncthreads();
-  // reserve this tile's room in every bin it touches; the slot then holds the next write position
-  for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) {
-    uint32_t v = sm_cnt[b];
-    if (v) sm_cnt[b] = atomicAdd(&cursor[b], v);
+  // reserve this tile's run in every bin it touches, then turn the counts into local start offsets
+  for (uint32_t b = t; b < n_coarse; b += blockDim.x) {
+    uint32_t v = run[b];
+    gbase[b] = v ? atomicAdd(&cursor[b], v) : 0;
   }
   __syncthreads();
-  for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
+  block_exclusive_scan(run, n_coarse, part);
+  for (uint32_t b = t; b < n_coarse; b += blockDim.x) gbase[b] -= run[b];     // global pos = gbase[bin] + local index
+  __syncthreads();
+  for (uint64_t i = first + t; i < last; i += blockDim.x)
     for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t val) {
-      uint32_t pos = atomicAdd(&sm_cnt[key >> lo_bits], 1u);
-      mid[pos] = make_uint2(key, val);
+      uint32_t pos = atomicAdd(&run[key >> lo_bits], 1u);
+      sm_stage[pos] = make_uint2(key, val);
     });
+  __syncthreads();
+  if (t == 0) total = run[n_coarse - 1];          // the last bin's cursor ends at the tile's entry count
+  __syncthreads();
+  for (uint32_t i = t; i < total; i += blockDim.x) {
+    uint2 e = sm_stage[i];
+    mid[gbase[e.x >> lo_bits] + i] = e;
+  }
 }
 
 // ---------------------------------------------------------------- C1: fine histograms of oversized bins
@@ -194,7 +238,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_fine_hist_kernel(const uint
     for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) cnt[f] = 0;
     __syncthreads();
     const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
-    const uint32_t s0 = b0 + w.y * kCap, s1 = s0 + kCap < b1 ? s0 + kCap : b1;
+    const uint32_t s0 = b0 + w.y * (kCap / 2), s1 = s0 + kCap / 2 < b1 ? s0 + kCap / 2 : b1;
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) atomicAdd(&cnt[mid[i].x & mask], 1u);
     __syncthreads();
     for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) {
@@ -236,6 +280,8 @@ __global__ void __launch_bounds__(1024) sort_fine_scan_kernel(const uint32_t* __
 }
 
 // ---------------------------------------------------------------- C2: final placement
+// dynamic shared memory: kCap / 2 loaded entries | kCap / 2 sorted entries | 2^lo_bits run cursors |
+// 2^lo_bits (global base - local start)
 __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* __restrict__ mid,
                                                                   const uint32_t* __restrict__ coarse_off,
                                                                   const uint2* __restrict__ items,
@@ -243,53 +289,48 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
                                                                   const uint32_t* __restrict__ bin_multi, uint32_t lo_bits,
                                                                   uint32_t* __restrict__ fine, uint32_t* __restrict__ keys_out,
                                                                   uint32_t* __restrict__ vals_out) {
-  extern __shared__ uint2 sm_ent[];                          // kCap entries, then 2^lo_bits counters
-  uint32_t* pos = reinterpret_cast<uint32_t*>(sm_ent + kCap);
+  extern __shared__ uint2 sm_ent[];                          // kCap/2 entries in, kCap/2 entries sorted
+  constexpr uint32_t kSeg = kCap / 2;
+  uint2* sorted = sm_ent + kSeg;
+  uint32_t* run = reinterpret_cast<uint32_t*>(sm_ent + kCap);
+  uint32_t* gbase = run + (1u << lo_bits);
   __shared__ uint32_t part[kPlaceThreads];
   for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
     const uint2 w = items[it];
     const uint32_t L = 1u << lo_bits, mask = L - 1, t = threadIdx.x;
-    for (uint32_t f = t; f < L; f += blockDim.x) pos[f] = 0;
+    for (uint32_t f = t; f < L; f += blockDim.x) run[f] = 0;
     __syncthreads();
     const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
-    const uint32_t s0 = b0 + w.y * kCap, s1 = s0 + kCap < b1 ? s0 + kCap : b1, cnt = s1 - s0;
+    const uint32_t s0 = b0 + w.y * kSeg, s1 = s0 + kSeg < b1 ? s0 + kSeg : b1, cnt = s1 - s0;
     for (uint32_t i = t; i < cnt; i += blockDim.x) {
       uint2 e = mid[s0 + i];
       sm_ent[i] = e;
-      atomicAdd(&pos[e.x & mask], 1u);
+      atomicAdd(&run[e.x & mask], 1u);
     }
     __syncthreads();
     if (bin_multi[w.x]) {
-      // shared bin: reserve this segment's share of every fine bucket in the global cursors
+      // shared bin: reserve this segment's run in every fine bucket from the global cursors
       for (uint32_t f = t; f < L; f += blockDim.x) {
-        uint32_t v = pos[f];
-        pos[f] = v ? atomicAdd(&fine[(uint64_t(w.x) << lo_bits) + f], v) : 0;
+        uint32_t v = run[f];
+        gbase[f] = v ? atomicAdd(&fine[(uint64_t(w.x) << lo_bits) + f], v) : 0;
       }
-    } else {
-      // private bin: exclusive scan of the fine counts, based at the bin's start
-      const uint32_t per = (L + kPlaceThreads - 1) / kPlaceThreads;
-      const uint32_t lo = t * per, hi = lo + per < L ? lo + per : L;
-      uint32_t sum = 0;
-      for (uint32_t f = lo; f < hi && f < L; f++) sum += pos[f];
-      part[t] = sum;
       __syncthreads();
-      for (uint32_t o = 1; o < kPlaceThreads; o <<= 1) {
-        uint32_t a = t >= o ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += a;
-        __syncthreads();
-      }
-      uint32_t off = b0 + part[t] - sum;
-      for (uint32_t f = lo; f < hi && f < L; f++) {
-        uint32_t v = pos[f];
-        pos[f] = off;
-        off += v;
-      }
+      block_exclusive_scan(run, L, part);
+      for (uint32_t f = t; f < L; f += blockDim.x) gbase[f] -= run[f];
+    } else {
+      // private bin: the local scan IS the layout of the bin's output region
+      block_exclusive_scan(run, L, part);
+      for (uint32_t f = t; f < L; f += blockDim.x) gbase[f] = b0;
     }
     __syncthreads();
     for (uint32_t i = t; i < cnt; i += blockDim.x) {
       uint2 e = sm_ent[i];
-      uint32_t p = atomicAdd(&pos[e.x & mask], 1u);
+      sorted[atomicAdd(&run[e.x & mask], 1u)] = e;
+    }
+    __syncthreads();
+    for (uint32_t i = t; i < cnt; i += blockDim.x) {
+      uint2 e = sorted[i];
+      uint32_t p = gbase[e.x & mask] + i;
       keys_out[p] = e.x;
       vals_out[p] = e.y;
     }
@@ -307,16 +348,16 @@ static uint32_t pow2_ceil(uint64_t x) {
 SortPlan msm_sort_plan(const MsmPlan& p) {
   SortPlan s{};
   const uint32_t kb = pow2_ceil(p.n_buckets);              // key space rounded up to a power of two
-  // coarse bins: average fill <= kCap / 3 so that private bins are the rule, and few enough for the
-  // shared counters of passes A / B; fine buckets per bin <= kMaxFine
-  uint32_t hb = pow2_ceil((p.m + kCap / 3 - 1) / (kCap / 3));
-  const uint32_t hb_min = kb > 12 ? kb - 12 : 0, hb_max = 14;
-  if (hb < hb_min) hb = hb_min;
+  // coarse bins: enough that small inputs get private bins (average fill <= a third of a segment),
+  // never more than kMaxCoarse (run length of pass B), and enough that a bin has <= kMaxFine buckets
+  uint32_t hb = pow2_ceil((p.m + kCap / 6 - 1) / (kCap / 6));
+  const uint32_t hb_min = kb > 12 ? kb - 12 : 0, hb_max = 11;
   if (hb > hb_max) hb = hb_max;
+  if (hb < hb_min) hb = hb_min;
   if (hb > kb) hb = kb;
   s.lo_bits = kb - hb;
   s.n_coarse = 1u << hb;
-  s.max_items = s.n_coarse + uint32_t(p.m / kCap) + 1;
+  s.max_items = s.n_coarse + uint32_t(p.m / (kCap / 2)) + 1;
   s.fine_entries = uint64_t(s.n_coarse) << s.lo_bits;
   return s;
 }
@@ -330,15 +371,15 @@ size_t msm_sort_scratch_bytes(const MsmPlan& p) {
 void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                                 uint32_t idx_base, int sm_count, cudaStream_t st) {
   const SortPlan s = msm_sort_plan(p);
-  const size_t place_smem = size_t(kCap) * 8 + (size_t(4) << s.lo_bits);
+  const size_t place_smem = size_t(kCap) * 8 + (size_t(8) << s.lo_bits);
+  const size_t scatter_smem = size_t(kCap) * 8 + size_t(8) * s.n_coarse;
   // opt-in to large dynamic shared memory, once per device of this process
   static std::once_flag configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(configured[dev & 63], [] {
-    cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxFine * 4));
-    cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxCoarse * 4));
-    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxCoarse * 4));
+    cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxFine * 8));
+    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxCoarse * 8));
   });
   if (b.ev) cudaEventRecord(b.ev[0], st);
   char* sc = reinterpret_cast<char*>(b.sort_temp);
@@ -360,18 +401,14 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
   d.val_stride = uint32_t(p.val_stride);
   d.idx_base = idx_base;
   d.one_set = p.val_stride != 0;
-  // tiles of passes A / B: enough entries per tile for the per-bin reservations to aggregate
-  // (>= 8 per coarse bin), and at least two waves of CTAs on large inputs
-  uint64_t per_cta = (uint64_t(8) * s.n_coarse + p.nwin - 1) / p.nwin;
-  if (per_cta < 2048) per_cta = 2048;
-  uint32_t tiles = uint32_t((n + per_cta - 1) / per_cta);
-  if (!tiles) tiles = 1;
-  const size_t csm = size_t(s.n_coarse) * 4;
-  sort_hist_kernel<<<tiles, kSortThreads, csm, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits,
-                                                     s.n_coarse, uint32_t(per_cta), coarse_hist, b.flag);
+  // pass A: any tiling does; pass B: a tile's entries (<= windows per scalar) must fit the staging area
+  const uint32_t per_a = 4096, per_b = kCap / p.nwin;
+  const uint32_t tiles_a = uint32_t((n + per_a - 1) / per_a), tiles_b = uint32_t((n + per_b - 1) / per_b);
+  sort_hist_kernel<<<tiles_a ? tiles_a : 1, kSortThreads, size_t(s.n_coarse) * 4, st>>>(
+      reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits, s.n_coarse, per_a, coarse_hist, b.flag);
   sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items, bin_multi);
-  sort_scatter_kernel<<<tiles, kSortThreads, csm, st>>>(reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits,
-                                                        s.n_coarse, uint32_t(per_cta), cursor, mid);
+  sort_scatter_kernel<<<tiles_b ? tiles_b : 1, kPlaceThreads, scatter_smem, st>>>(
+      reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);
   if (b.ev) cudaEventRecord(b.ev[1], st);
   const uint32_t grid_c = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;
   sort_fine_hist_kernel<<<grid_c, kSortThreads, 0, st>>>(mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine);

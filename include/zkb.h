@@ -58,8 +58,9 @@ int zkb_ctx_sync(zkb_ctx* ctx);
  * "assemble_on_device" (0/1, see zkb_groth16_assemble_host),
  * "msm_sort" (process-wide, default 0 = the library's own bucket sort fused with digit extraction;
  * 1 = digits kernel + cub::DeviceRadixSort, kept as the comparison baseline),
- * "msm_g2_pair" (process-wide, default 0; 1 = the G2 bucket walk splits each Fq2 point operation
- * over a lane pair — measured slower than one thread per point on B200, kept for comparison) */
+ * "msm_g2_pair" (process-wide bit mask, default 2: bit 1 = the latency-bound G2 kernels around the
+ * bucket walk run one Fq2 operation per lane PAIR; bit 0 = the walk itself does too — measured 5 %
+ * slower than one thread per point on B200, kept for comparison) */
 int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value);
 const char* zkb_version(void);
 /* page-locked (pinned, portable) host memory for witnesses / scalars: H2D copies from it run at PCIe

@@ -1,5 +1,7 @@
-"""G2 bucket walk: one Fq2 point operation per lane PAIR (Fq2L, 16 warps / SM) against the
-one-thread-per-point walk (255 registers, 8 warps / SM).  Same bases, same scalars, same result."""
+"""G2 MSM variants behind the "msm_g2_pair" switch: bit 0 = bucket WALK with one Fq2 point operation per
+lane pair (Fq2L, 16 warps / SM) instead of one thread per point (255 registers, 8 warps / SM); bit 1 =
+the latency-bound kernels around the walk on lane pairs instead of out-of-line Fq2 products.
+Same bases, same scalars, same result."""
 import json, os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,7 +22,9 @@ stream = torch.cuda.ExternalStream(ctx.stream)
 res = {}
 pipe = ctx.bench_int_pipe(3000)
 ctx.set("msm_profile", 1)
-for pair in (0, 1, 0, 1):
+ctx.set("msm_g2_pair", 2)
+MODES = {0: "walk_single_tails_calls", 2: "walk_single_tails_pair", 1: "walk_pair_tails_calls", 3: "walk_pair_tails_pair"}
+for pair in (0, 2, 1, 3, 0, 2):
     ctx.set("msm_g2_pair", pair)
     for _ in range(2):
         ctx.msm_dev(bases, sc.data_ptr(), n, out.data_ptr())
@@ -34,7 +38,7 @@ for pair in (0, 1, 0, 1):
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
         l1.append(ctx.msm_last_timings()["accumulate_l1"])
-    key = "pair" if pair else "single"
+    key = MODES[pair]
     res.setdefault(key, {"msm_ms": [], "walk_ms": [], "result": None})
     res[key]["msm_ms"].append(statistics.median(ts))
     res[key]["walk_ms"].append(statistics.median(l1))
@@ -43,11 +47,11 @@ for pair in (0, 1, 0, 1):
 c = bases.window
 nwin = (255 + c - 1) // c
 imads = n * nwin * (8 * 400 + 2 * 272)          # 8 Fq2 products + 2 Fq2 squarings per mixed addition
-for k, v in res.items():
+for k, v in list(res.items()):
     v["walk_frac_int_pipe"] = imads / (min(v["walk_ms"]) * 1e-3) / pipe["imad_wide_per_s"]
-res["same_result"] = res["pair"]["result"] == res["single"]["result"]
+res["same_result"] = len({v["result"] for v in res.values()}) == 1
 res["window_bits"], res["windows"], res["log_n"], res["imad_wide_per_s"] = c, nwin, log_n, pipe["imad_wide_per_s"]
-for k in ("pair", "single"):
+for k in MODES.values():
     res[k]["result"] = res[k]["result"][:16] + "..."
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "g2_pair_time_2p%d.json" % log_n), "w"), indent=1)
