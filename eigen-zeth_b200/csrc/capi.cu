@@ -460,27 +460,80 @@ int msm_exec_prove(zkb_ctx* ctx, const zkb_bases* a, const zkb_bases* b1, const 
   if ((rc = ensure_msm_buffers(ctx, ph, &buf))) return rc;
   if ((rc = ensure_msm_buffers(ctx, p1, &buf))) return rc;
   if ((rc = ensure_msm_buffers(ctx, pt, &buf, false))) return rc;
-  ZKB_CUDA(ctx, ctx->msm.buckets2.ensure(p2.n_buckets * p2.point_bytes));
+  MsmScratch& sc = ctx->msm;
+  ZKB_CUDA(ctx, sc.buckets2.ensure(p2.n_buckets * p2.point_bytes));
+  // Order on the main stream: sort(z), the four witness walks, sort(h), the H walk — each walk is
+  // one resident wave that owns every register of the GPU, nothing overlaps it.  What follows is
+  // latency-bound (partial merges, bucket reductions, window sums, Horner: small grids of dependent
+  // point additions) and runs side by side: one stream per MSM for its partial merges, then the
+  // shared G1 tail on the main stream next to the G2 tail on its own.
+  const MsmPlan* plans[5] = {&p1, &p1, &p1, &p2, &ph};
+  size_t part_off[6] = {0};
+  for (int j = 0; j < 5; j++) {
+    const MsmPlan& q = *plans[j];
+    const size_t bytes = 2ull * q.l1_threads * (4 + q.point_bytes) + 2ull * q.l2_threads * (4 + q.point_bytes) + 1024;
+    part_off[j + 1] = part_off[j] + ((bytes + 255) & ~size_t(255));
+  }
+  ZKB_CUDA(ctx, sc.multi_part.ensure(part_off[5]));
+  ZKB_CUDA(ctx, sc.group_sums2.ensure((p2.red_run_total + uint64_t(p2.n_sets) * ((p2.half + 15) / 16 + 64)) * p2.point_bytes));
+  ZKB_CUDA(ctx, sc.window_sums2.ensure(uint64_t(p2.red_levels + 2) * p2.n_sets * p2.point_bytes));
+  for (int j = 0; j < 5; j++)
+    if (!ctx->side[j]) ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[j], cudaStreamNonBlocking));
+  for (int j = 0; j < 6; j++)
+    if (!ctx->side_ev[j]) ZKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->side_ev[j], cudaEventDisableTiming));
+  MsmBuffers bj[5];
+  for (int j = 0; j < 5; j++) {
+    const MsmPlan& q = *plans[j];
+    bj[j] = buf;
+    bj[j].ev = nullptr;
+    char* base = (char*)sc.multi_part.p + part_off[j];
+    bj[j].part1_keys = (uint32_t*)base;
+    base += (2ull * q.l1_threads * 4 + 255) & ~size_t(255);
+    bj[j].part1_pts = base;
+    base += 2ull * q.l1_threads * q.point_bytes;
+    bj[j].part2_keys = (uint32_t*)base;
+    base += (2ull * q.l2_threads * 4 + 255) & ~size_t(255);
+    bj[j].part2_pts = base;
+  }
   cudaStream_t st = ctx->stream;
   char* g1b = (char*)buf.buckets;
   const size_t set_bytes = size_t(p1.half) * p1.point_bytes;
+  void* targets[5] = {g1b, g1b + set_bytes, g1b + 2 * set_bytes, sc.buckets2.p, g1b + 3 * set_bytes};
   msm_digits_and_sort(p1, buf, d_z, nz, 0, st);
-  msm_accumulate_g1(p1, buf, a->d_pts, g1b, st);
+  msm_walk_g1(p1, bj[0], a->d_pts, targets[0], st);
   if (ev4_opt) cudaEventRecord(ev4_opt[0], st);
-  msm_accumulate_g1(p1, buf, b1->d_pts, g1b + set_bytes, st);
+  msm_walk_g1(p1, bj[1], b1->d_pts, targets[1], st);
   if (ev4_opt) cudaEventRecord(ev4_opt[1], st);
-  msm_accumulate_g1(p1, buf, l->d_pts, g1b + 2 * set_bytes, st);
+  msm_walk_g1(p1, bj[2], l->d_pts, targets[2], st);
   if (ev4_opt) cudaEventRecord(ev4_opt[2], st);
-  msm_accumulate_g2(p2, buf, b2->d_pts, ctx->msm.buckets2.p, st);
+  msm_walk_g2(p2, bj[3], b2->d_pts, targets[3], st);
   if (ev4_opt) cudaEventRecord(ev4_opt[3], st);
   msm_digits_and_sort(ph, buf, d_h, nh, 0, st);
-  msm_accumulate_g1(ph, buf, h->d_pts, g1b + 3 * set_bytes, st);
+  msm_walk_g1(ph, bj[4], h->d_pts, targets[4], st);
+  ZKB_CUDA(ctx, cudaEventRecord(ctx->side_ev[5], st));
+  for (int j = 0; j < 5; j++) {
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[j], ctx->side_ev[5], 0));
+    if (j == 3) {
+      msm_post_g2(p2, bj[3], targets[3], ctx->side[3]);
+      MsmBuffers buf2 = buf;                 // the G2 tail right behind its merges, on its own scratch
+      buf2.ev = nullptr;
+      buf2.buckets = sc.buckets2.p;
+      buf2.group_sums = sc.group_sums2.p;
+      buf2.window_sums = sc.window_sums2.p;
+      buf2.result_affine = res + 128;
+      msm_tail_g2(p2, buf2, ctx->side[3]);
+    } else {
+      msm_post_g1(*plans[j], bj[j], targets[j], ctx->side[j]);
+    }
+    ZKB_CUDA(ctx, cudaEventRecord(ctx->side_ev[j], ctx->side[j]));
+  }
+  for (int j = 0; j < 5; j++)
+    if (j != 3) ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_ev[j], 0));
   void* outs[4] = {res, res + 64, res + 256, res + 320};
-  msm_tail_multi_g1(pt, buf, outs, 4, st);
-  MsmBuffers buf2 = buf;
-  buf2.buckets = ctx->msm.buckets2.p;
-  buf2.result_affine = res + 128;
-  msm_tail_g2(p2, buf2, st);
+  MsmBuffers buft = buf;
+  buft.ev = nullptr;
+  msm_tail_multi_g1(pt, buft, outs, 4, st);
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_ev[3], 0));
   ZKB_CUDA(ctx, cudaGetLastError());
   return ZKB_OK;
 }
@@ -842,6 +895,13 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
   for (int i = 0; i < 16; i++)
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 5; i++)
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+  for (int i = 0; i < 6; i++)
+    if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
+  ctx->msm.multi_part.release();
+  ctx->msm.group_sums2.release();
+  ctx->msm.window_sums2.release();
   ctx->msm.buckets2.release();
   ctx->msm.flag.release();
   cudaStreamDestroy(ctx->stream);

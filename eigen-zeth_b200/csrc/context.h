@@ -55,6 +55,9 @@ struct CosetTables {        // per log_n
 
 struct MsmScratch {
   DevBuf buckets2, flag;
+  // one proof = five MSMs whose latency-bound phases run side by side: partial lists per MSM and a
+  // second set of tail scratch for the G2 reduction
+  DevBuf multi_part, group_sums2, window_sums2;
   DevBuf keys_in, vals_in, keys_out, vals_out, sort_temp, m_valid, buckets, part1_keys,
       part1_pts, part2_keys, part2_pts, group_sums, window_sums, result_xyzz, result_affine;
 };
@@ -83,6 +86,8 @@ struct zkb_ctx {
   int64_t msm_host_chunks = 0;             // 0 = auto
   int64_t pk_precompute = 1;               // proving-key queries carry precomputed window multiples
   int64_t assemble_on_device = 0;          // 1: the one-CTA assembly kernel instead of the host ladders (comparison)
+  cudaStream_t side[5] = {};               // latency-bound MSM phases of one proof, one stream per MSM
+  cudaEvent_t side_ev[6] = {};
   cudaStream_t copy_stream = nullptr;      // H2D of scalar chunks, overlapped with compute
   cudaEvent_t copy_ev[16] = {};
   cudaEvent_t msm_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

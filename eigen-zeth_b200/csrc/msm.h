@@ -90,6 +90,13 @@ void msm_accumulate_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_base
                        cudaStream_t s);
 void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target,
                        cudaStream_t s);
+// the two halves of msm_accumulate_*: the level-1 walk (throughput-bound, owns the GPU) and the
+// reduction of its partial list into the buckets (short latency-bound launches that can share the
+// GPU with those of other MSMs on other streams); both use b.part1_* / b.part2_*
+void msm_walk_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target, cudaStream_t s);
+void msm_walk_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target, cudaStream_t s);
+void msm_post_g1(const MsmPlan& p, const MsmBuffers& b, void* bucket_target, cudaStream_t s);
+void msm_post_g2(const MsmPlan& p, const MsmBuffers& b, void* bucket_target, cudaStream_t s);
 void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s);
 void msm_tail_g1(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s);

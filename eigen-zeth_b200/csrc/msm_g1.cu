@@ -6,6 +6,12 @@ void msm_accumulate_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_base
                        cudaStream_t s) {
   msm_accumulate_t<Fq>(p, b, d_bases, bucket_target, s);
 }
+void msm_walk_g1(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target, cudaStream_t s) {
+  msm_walk_t<Fq>(p, b, d_bases, bucket_target, s);
+}
+void msm_post_g1(const MsmPlan& p, const MsmBuffers& b, void* bucket_target, cudaStream_t s) {
+  msm_post_t<Fq>(p, b, bucket_target, s);
+}
 void msm_merge_g1(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
   msm_merge_t<Fq>(p, main_buckets, part_buckets, s);
 }

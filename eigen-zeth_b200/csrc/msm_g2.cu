@@ -21,11 +21,19 @@ void msm_accumulate_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_base
   else if (pair_tail) msm_accumulate_t<Fq2, Fq2, Fq2L>(p, b, d_bases, bucket_target, s);
   else msm_accumulate_t<Fq2, Fq2, Fq2C>(p, b, d_bases, bucket_target, s);
 }
+void msm_walk_g2(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target, cudaStream_t s) {
+  if (p.g2_pair & 1) msm_walk_t<Fq2, Fq2L>(p, b, d_bases, bucket_target, s);
+  else msm_walk_t<Fq2, Fq2>(p, b, d_bases, bucket_target, s);
+}
+void msm_post_g2(const MsmPlan& p, const MsmBuffers& b, void* bucket_target, cudaStream_t s) {
+  if (p.g2_pair & 2) msm_post_t<Fq2, Fq2L>(p, b, bucket_target, s);
+  else msm_post_t<Fq2, Fq2C>(p, b, bucket_target, s);
+}
 void msm_merge_g2(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
   msm_merge_t<Fq2C>(p, main_buckets, part_buckets, s);
 }
 void msm_tail_g2(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s) {
-  if (p.g2_pair & 2) msm_tail_t<Fq2L>(p, b, s);
+  if (p.g2_pair & 2) msm_tail_t<Fq2L, Fq2C>(p, b, s);
   else msm_tail_t<Fq2C>(p, b, s);
 }
 void msm_bases_to_mont_g2(void* d_pts, uint64_t n, const uint32_t* b_mont, uint32_t* d_flag, cudaStream_t s) {

@@ -339,12 +339,11 @@ __global__ void __launch_bounds__(128) msm_bucket_merge_kernel(XYZZ<F>* __restri
 // sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first).
 // FW is the register-level field type of the level-1 walk, FT that of the latency-bound kernels
 // after it (F itself, or a type with the same storage layout: Fq2C / Fq2L for F = Fq2).
-template <class F, class FW = F, class FT = F>
-void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases,
-                      void* bucket_target, cudaStream_t s) {
-  static_assert(F::kBytes == FW::kBytes && F::kBytes == FT::kBytes, "walk types must share the storage layout");
+// level-1 walk only: sorted stream -> whole buckets in `bucket_target` + 2 partials per chunk in b.part1_*
+template <class F, class FW = F>
+void msm_walk_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases, void* bucket_target, cudaStream_t s) {
+  static_assert(F::kBytes == FW::kBytes, "walk types must share the storage layout");
   constexpr size_t kPt = 4 * size_t(F::kBytes);
-  constexpr uint32_t L = FT::kLanes;
   cudaMemsetAsync(bucket_target, 0, p.n_buckets * kPt, s);
   msm_accumulate_l1_kernel<FW><<<(p.l1_threads * FW::kLanes + 127) / 128, 128, 0, s>>>(
       b.keys_out, b.vals_out, b.m_valid, reinterpret_cast<const char*>(d_bases),
@@ -352,10 +351,16 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
       p.l1_threads);
   count_launches(1);
   if (b.ev) cudaEventRecord(b.ev[3], s);
-  // the partial list shrinks 16x per level-2 pass (chunks of l2_len entries -> 2 partials); passes
-  // repeat, ping-ponging between the two partial buffers, until the list is short enough for the
-  // serial-per-run finish.  A single giant bucket (0/1 witnesses, all-equal scalars) therefore
-  // costs a few short passes, never a long serial chain.
+}
+
+// the partial list of a walk -> buckets.  The list shrinks 16x per level-2 pass (chunks of l2_len
+// entries -> 2 partials); passes repeat, ping-ponging between the two partial buffers, until the
+// list is short enough for the serial-per-run finish.  A single giant bucket (0/1 witnesses,
+// all-equal scalars) therefore costs a few short passes, never a long serial chain.
+template <class F, class FT = F>
+void msm_post_t(const MsmPlan& p, const MsmBuffers& b, void* bucket_target, cudaStream_t s) {
+  static_assert(F::kBytes == FT::kBytes, "types must share the storage layout");
+  constexpr uint32_t L = FT::kLanes;
   uint32_t* keys_a = b.part1_keys;
   uint32_t* keys_b = b.part2_keys;
   char* pts_a = reinterpret_cast<char*>(b.part1_pts);
@@ -376,6 +381,16 @@ void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases
   if (b.ev) cudaEventRecord(b.ev[4], s);
 }
 
+// sorted (key, value) stream -> bucket sums written to `bucket_target` (cleared first).
+// FW is the register-level field type of the level-1 walk, FT that of the latency-bound kernels
+// after it (F itself, or a type with the same storage layout: Fq2C / Fq2L for F = Fq2).
+template <class F, class FW = F, class FT = F>
+void msm_accumulate_t(const MsmPlan& p, const MsmBuffers& b, const void* d_bases,
+                      void* bucket_target, cudaStream_t s) {
+  msm_walk_t<F, FW>(p, b, d_bases, bucket_target, s);
+  msm_post_t<F, FT>(p, b, bucket_target, s);
+}
+
 template <class F>
 void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets, cudaStream_t s) {
   using P = XYZZ<F>;
@@ -387,8 +402,13 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
 // bucket sums -> one point (Montgomery XYZZ + canonical affine)
 // scratch layout in b.group_sums (points): [runs of all levels][w0 of one level][stage 64*n_sets]
 // b.window_sums: [levels][n_sets] W_l, [n_sets] S, [n_sets] set sums
-template <class F>
+// F: register-level type of the latency-bound launches; FB: of a reduce level with so many groups
+// (>= kBigLevel work items) that it is throughput-bound (G2: lane pairs lose there, 2.87 vs 2.36 ms
+// at 2^19 buckets, and win below, 1.18 vs 1.73 ms at 2^16)
+constexpr uint32_t kBigLevel = 16384;
+template <class F, class FB = F>
 void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const MsmOutPtrs* independent = nullptr) {
+  static_assert(F::kBytes == FB::kBytes, "tail types must share the storage layout");
   constexpr size_t kPt = 4 * size_t(F::kBytes);
   constexpr uint32_t L = F::kLanes;
   char* scratch = reinterpret_cast<char*>(b.group_sums);
@@ -404,7 +424,10 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const Msm
     groups = (count + kRedGroup - 1) / kRedGroup;
     uint32_t threads = groups * p.n_sets;
     const int last = l + 1 == p.red_levels;
-    msm_reduce_level_kernel<F><<<(threads * L + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
+    if (threads >= kBigLevel)
+      msm_reduce_level_kernel<FB><<<(threads * FB::kLanes + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
+    else
+      msm_reduce_level_kernel<F><<<(threads * L + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
     // W_l[set] = sum of this level's w0 (two-stage when there are many)
     const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
     char* wl_out = wl + uint64_t(l) * p.n_sets * kPt;

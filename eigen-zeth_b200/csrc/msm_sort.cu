@@ -280,8 +280,10 @@ __global__ void __launch_bounds__(1024) sort_fine_scan_kernel(const uint32_t* __
 }
 
 // ---------------------------------------------------------------- C2: final placement
-// dynamic shared memory: kCap / 2 loaded entries | kCap / 2 sorted entries | 2^lo_bits run cursors |
-// 2^lo_bits (global base - local start)
+// dynamic shared memory: kSeg sorted entries | 2^lo_bits run cursors | 2^lo_bits (global base - local
+// start).  The segment is read twice from global memory (count, then place: the second read hits L2)
+// rather than staged, so that two CTAs fit on an SM.
+constexpr uint32_t kSeg = kCap / 2;
 __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* __restrict__ mid,
                                                                   const uint32_t* __restrict__ coarse_off,
                                                                   const uint2* __restrict__ items,
@@ -289,10 +291,8 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
                                                                   const uint32_t* __restrict__ bin_multi, uint32_t lo_bits,
                                                                   uint32_t* __restrict__ fine, uint32_t* __restrict__ keys_out,
                                                                   uint32_t* __restrict__ vals_out) {
-  extern __shared__ uint2 sm_ent[];                          // kCap/2 entries in, kCap/2 entries sorted
-  constexpr uint32_t kSeg = kCap / 2;
-  uint2* sorted = sm_ent + kSeg;
-  uint32_t* run = reinterpret_cast<uint32_t*>(sm_ent + kCap);
+  extern __shared__ uint2 sorted[];
+  uint32_t* run = reinterpret_cast<uint32_t*>(sorted + kSeg);
   uint32_t* gbase = run + (1u << lo_bits);
   __shared__ uint32_t part[kPlaceThreads];
   for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
@@ -302,11 +302,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
     __syncthreads();
     const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
     const uint32_t s0 = b0 + w.y * kSeg, s1 = s0 + kSeg < b1 ? s0 + kSeg : b1, cnt = s1 - s0;
-    for (uint32_t i = t; i < cnt; i += blockDim.x) {
-      uint2 e = mid[s0 + i];
-      sm_ent[i] = e;
-      atomicAdd(&run[e.x & mask], 1u);
-    }
+    for (uint32_t i = t; i < cnt; i += blockDim.x) atomicAdd(&run[mid[s0 + i].x & mask], 1u);
     __syncthreads();
     if (bin_multi[w.x]) {
       // shared bin: reserve this segment's run in every fine bucket from the global cursors
@@ -324,7 +320,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
     }
     __syncthreads();
     for (uint32_t i = t; i < cnt; i += blockDim.x) {
-      uint2 e = sm_ent[i];
+      uint2 e = mid[s0 + i];
       sorted[atomicAdd(&run[e.x & mask], 1u)] = e;
     }
     __syncthreads();
@@ -371,14 +367,14 @@ size_t msm_sort_scratch_bytes(const MsmPlan& p) {
 void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                                 uint32_t idx_base, int sm_count, cudaStream_t st) {
   const SortPlan s = msm_sort_plan(p);
-  const size_t place_smem = size_t(kCap) * 8 + (size_t(8) << s.lo_bits);
+  const size_t place_smem = size_t(kSeg) * 8 + (size_t(8) << s.lo_bits);
   const size_t scatter_smem = size_t(kCap) * 8 + size_t(8) * s.n_coarse;
   // opt-in to large dynamic shared memory, once per device of this process
   static std::once_flag configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(configured[dev & 63], [] {
-    cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxFine * 8));
+    cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kSeg) * 8 + kMaxFine * 8));
     cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxCoarse * 8));
   });
   if (b.ev) cudaEventRecord(b.ev[0], st);
@@ -413,7 +409,8 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
   const uint32_t grid_c = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;
   sort_fine_hist_kernel<<<grid_c, kSortThreads, 0, st>>>(mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine);
   sort_fine_scan_kernel<<<s.n_coarse < 296 ? s.n_coarse : 296, 1024, 0, st>>>(coarse_off, bin_multi, s.n_coarse, s.lo_bits, fine);
-  sort_place_kernel<<<uint32_t(sm_count) < s.max_items ? uint32_t(sm_count) : s.max_items, kPlaceThreads, place_smem, st>>>(
+  const uint32_t grid_p = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;
+  sort_place_kernel<<<grid_p, kPlaceThreads, place_smem, st>>>(
       mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine, b.keys_out, b.vals_out);
   count_launches(6);
   if (b.ev) cudaEventRecord(b.ev[2], st);
