@@ -950,6 +950,11 @@ int zkb_ctx_set(zkb_ctx* ctx, const char* key, int64_t value) {
     ctx->msm_host_chunks = value;
     return ZKB_OK;
   }
+  if (!std::strcmp(key, "pk_window")) {
+    if (value != 0 && (value < 8 || value > 24)) return set_error(ctx, ZKB_EINVAL, "pk_window must be 0 or 8..24");
+    ctx->pk_window = value;
+    return ZKB_OK;
+  }
   if (!std::strcmp(key, "assemble_on_device")) {
     ctx->assemble_on_device = value ? 1 : 0;
     return ZKB_OK;

@@ -85,6 +85,7 @@ struct zkb_ctx {
   int64_t msm_profile = 0;
   int64_t msm_host_chunks = 0;             // 0 = auto
   int64_t pk_precompute = 1;               // proving-key queries carry precomputed window multiples
+  int64_t pk_window = 0;                   // window width of proving-key queries (0 = by size, msm_auto_window)
   int64_t assemble_on_device = 0;          // 1: the one-CTA assembly kernel instead of the host ladders (comparison)
   cudaStream_t side[5] = {};               // latency-bound MSM phases of one proof, one stream per MSM
   cudaEvent_t side_ev[6] = {};

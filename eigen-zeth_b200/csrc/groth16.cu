@@ -516,7 +516,7 @@ int zkb_pk_synthetic_shard_ex(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint3
     if (ctx->pk_precompute) {
       zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
       for (zkb_bases* q : qs)
-        if (q->n && (rc = bases_precompute_nolock(ctx, q, 0))) throw rc;
+        if (q->n && (rc = bases_precompute_nolock(ctx, q, int(ctx->pk_window)))) throw rc;
     }
     // fixed points: [alpha, beta, delta, ic0, ic1] * G1 and [beta, delta, gamma] * G2
     std::vector<uint64_t> f1(4 * 5), f2(4 * 3);
@@ -657,7 +657,7 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     if (ctx->pk_precompute) {
       zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
       for (zkb_bases* q : qs)
-        if (q->n && (rc = bases_precompute_nolock(ctx, q, 0))) throw rc;
+        if (q->n && (rc = bases_precompute_nolock(ctx, q, int(ctx->pk_window)))) throw rc;
     }
     // fixed points -> Montgomery on device: alpha_g1 | beta_g1 | delta_g1 | beta_g2 | delta_g2
     uint8_t f1[192], f2[256];

@@ -185,8 +185,14 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t* __restr
 // 16-way level first; the (last) level then folds 16 g run_g in with a small scalar multiplication.
 constexpr uint32_t kRedGroup = 16;
 
+// resident CTAs per SM the reduce level is compiled for: a level over 2^19..2^21 buckets is
+// throughput-bound, and unconstrained ptxas gives the G1 form 202 registers = 8 warps / SM; capped at
+// 168 registers (a few spills) it runs 12 warps / SM.  The G2 forms need every register they can get.
+template <class F> struct ReduceCfg { static constexpr int kMinBlocks = 1; };
+template <> struct ReduceCfg<Fq> { static constexpr int kMinBlocks = 3; };
+
 template <class F>
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const char* __restrict__ in,
+__global__ void __launch_bounds__(128, ReduceCfg<F>::kMinBlocks) msm_reduce_level_kernel(const char* __restrict__ in,
                                                                uint32_t count, uint32_t groups,
                                                                uint32_t n_sets, char* __restrict__ run_out,
                                                                char* __restrict__ w0_out, int last_level) {

@@ -55,6 +55,7 @@ void* zkb_ctx_stream(zkb_ctx* ctx);                 /* cudaStream_t */
 int zkb_ctx_sync(zkb_ctx* ctx);
 /* tunables: "msm_window" (0 = auto), "ntt_full_twiddles" (0/1), "msm_profile" (0/1),
  * "msm_host_chunks" (0 = auto, 1..16), "pk_precompute" (0/1: window multiples for proving keys),
+ * "pk_window" (0 = by size; 8..24: window width of the queries of keys created afterwards),
  * "assemble_on_device" (0/1, see zkb_groth16_assemble_host),
  * "msm_sort" (process-wide, default 0 = the library's own bucket sort fused with digit extraction;
  * 1 = digits kernel + cub::DeviceRadixSort, kept as the comparison baseline),
