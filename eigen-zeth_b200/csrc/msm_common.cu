@@ -91,10 +91,11 @@ int msm_auto_window(uint64_t n, bool precomputed) {
   if (precomputed) {
     // ONE bucket set shared by all windows: the width can grow until the bucket reduction
     // (2 adds per bucket) shows.  Only the smallest c of each window count ceil(255/c) is useful.
-    // Calibrated on B200 (tools/tune_window.py, profiles/r01_tune_window.json).
+    // Calibrated on B200 (tools/tune_window.py, profiles/r01_tune_window.json; re-checked on whole proofs
+    // with the batched / concurrent tails of round 2: tools/tune_prove_window.py).
     if (log_n <= 14) return 11;   // 24 windows
     if (log_n <= 16) return 15;   // 17
-    if (log_n <= 19) return 17;   // 15
+    if (log_n <= 20) return 17;   // 15  (2^20: 17 beats 20 by 4 % inside a proof, profiles/r02_tune_prove_window.json)
     if (log_n <= 22) return 20;   // 13
     return 22;                    // 12
   }
