@@ -305,7 +305,7 @@ static int ensure_msm_buffers(zkb_ctx* ctx, const MsmPlan& p, MsmBuffers* b, boo
   ZKB_CUDA(ctx, s.part1_pts.ensure(2ull * p.l1_threads * p.point_bytes));
   ZKB_CUDA(ctx, s.part2_keys.ensure(2ull * p.l2_threads * 4));
   ZKB_CUDA(ctx, s.part2_pts.ensure(2ull * p.l2_threads * p.point_bytes));
-  ZKB_CUDA(ctx, s.group_sums.ensure((p.red_run_total + uint64_t(p.n_sets) * ((p.half + 15) / 16 + 64)) * p.point_bytes));
+  ZKB_CUDA(ctx, s.group_sums.ensure(msm_tail_scratch_points(p) * p.point_bytes));
   ZKB_CUDA(ctx, s.window_sums.ensure(uint64_t(p.red_levels + 2) * p.n_sets * p.point_bytes));
   ZKB_CUDA(ctx, s.result_xyzz.ensure(p.point_bytes));
   ZKB_CUDA(ctx, s.result_affine.ensure(p.point_bytes / 2));
@@ -475,7 +475,7 @@ int msm_exec_prove(zkb_ctx* ctx, const zkb_bases* a, const zkb_bases* b1, const 
     part_off[j + 1] = part_off[j] + ((bytes + 255) & ~size_t(255));
   }
   ZKB_CUDA(ctx, sc.multi_part.ensure(part_off[5]));
-  ZKB_CUDA(ctx, sc.group_sums2.ensure((p2.red_run_total + uint64_t(p2.n_sets) * ((p2.half + 15) / 16 + 64)) * p2.point_bytes));
+  ZKB_CUDA(ctx, sc.group_sums2.ensure(msm_tail_scratch_points(p2) * p2.point_bytes));
   ZKB_CUDA(ctx, sc.window_sums2.ensure(uint64_t(p2.red_levels + 2) * p2.n_sets * p2.point_bytes));
   for (int j = 0; j < 5; j++)
     if (!ctx->side[j]) ZKB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[j], cudaStreamNonBlocking));

@@ -62,6 +62,12 @@ struct MsmBuffers {
 // (c_override is then the width they were built for) and all windows share one bucket set.
 MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint64_t precomp_stride = 0);
 int msm_auto_window(uint64_t n, bool precomputed);
+// tail (msm_tail_t): partial sums a point array of `count` entries per set is cut into, and the XYZZ
+// points of b.group_sums the plan's tail needs (runs + w0 of every level + the partials)
+inline uint32_t msm_tail_slices(uint32_t count) {
+  return count >= 65536 ? 256 : (count >= 4096 ? 64 : (count >= 256 ? 8 : 1));
+}
+uint64_t msm_tail_scratch_points(const MsmPlan& p);
 // resident threads per SM the level-1 walk kernel of each curve is compiled for (launch bounds)
 uint32_t msm_l1_threads_per_sm_g1();
 uint32_t msm_l1_threads_per_sm_g2(int pair);

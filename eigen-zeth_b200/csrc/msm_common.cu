@@ -146,6 +146,17 @@ MsmPlan msm_make_plan(uint64_t n, int is_g2, int c_override, int sm_count, uint6
 }
 
 
+uint64_t msm_tail_scratch_points(const MsmPlan& p) {
+  uint64_t stage = 0;
+  uint32_t cnt = p.half;
+  for (uint32_t l = 0; l < p.red_levels; l++) {
+    cnt = (cnt + 15) / 16;
+    stage += uint64_t(msm_tail_slices(cnt)) * p.n_sets;       // this level's w0
+  }
+  stage += uint64_t(msm_tail_slices(cnt)) * p.n_sets;         // the last level's runs
+  return 2 * p.red_run_total + stage;
+}
+
 void msm_digits_and_sort(const MsmPlan& p, const MsmBuffers& b, const void* d_scalars, uint64_t n,
                          uint32_t idx_base, cudaStream_t s) {
   if (p.sort_mode == 0) {

@@ -216,17 +216,29 @@ __global__ void __launch_bounds__(128, ReduceCfg<F>::kMinBlocks) msm_reduce_leve
 }
 
 // ---------------------------------------------------------------- 7. window sum
-// CTA (set, slice) sums its slice of the `count` points of a set (serial per item, then a shared
-// memory tree over the blockDim.x / kLanes items).  Launched twice: group sums -> `slices` partials
-// per set -> one point per set.
+// One launch sums SEVERAL point arrays at once (the w0's of every reduce level and the runs of the
+// last one: independent, latency-bound sums that used to be one launch pair each).  CTA (job, set,
+// slice) sums its slice of the `count` points of a set (serial per item, then a shared memory tree
+// over the blockDim.x / kLanes items) and writes point [set * slices + slice] of the job's output.
+// Launched twice: inputs -> `slices` partials per set -> one point per set.
+constexpr uint32_t kMaxSumJobs = 4;
+struct SumJobs {
+  const char* in[kMaxSumJobs];
+  char* out[kMaxSumJobs];
+  uint32_t count[kMaxSumJobs], slices[kMaxSumJobs], first[kMaxSumJobs + 1];   // first[j] = first CTA of job j
+  uint32_t n;
+};
+
 template <class F>
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const char* __restrict__ in,
-                                                             uint32_t count, uint32_t slices,
-                                                             char* __restrict__ out) {
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(SumJobs jobs) {
   extern __shared__ uint4 sm_raw[];
   char* sm = reinterpret_cast<char*>(sm_raw);
+  uint32_t j = 0;
+  while (j + 1 < jobs.n && blockIdx.x >= jobs.first[j + 1]) j++;
+  const char* in = jobs.in[j];
+  const uint32_t count = jobs.count[j], slices = jobs.slices[j], local = blockIdx.x - jobs.first[j];
   const uint32_t items = blockDim.x / F::kLanes;
-  const uint32_t set = blockIdx.x / slices, slice = blockIdx.x - set * slices, t = threadIdx.x / F::kLanes;
+  const uint32_t set = local / slices, slice = local - set * slices, t = threadIdx.x / F::kLanes;
   const uint32_t len = (count + slices - 1) / slices;
   const uint32_t lo = slice * len, hi = lo + len < count ? lo + len : count;
   XYZZ<F> acc = XYZZ<F>::infinity();
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const char* __restr
     }
     __syncthreads();
   }
-  if (t == 0) st_pt<F>(ld_pt<F>(sm, 0), out, blockIdx.x);
+  if (t == 0) st_pt<F>(ld_pt<F>(sm, 0), jobs.out[j], local);
 }
 
 // ---------------------------------------------------------------- 8. Horner + output
@@ -406,7 +418,8 @@ void msm_merge_t(const MsmPlan& p, void* main_buckets, const void* part_buckets,
 }
 
 // bucket sums -> one point (Montgomery XYZZ + canonical affine)
-// scratch layout in b.group_sums (points): [runs of all levels][w0 of one level][stage 64*n_sets]
+// scratch layout in b.group_sums (points): [runs of all levels][w0 of all levels][stage: slices * n_sets
+// per summed array] (msm_tail_scratch_points)
 // b.window_sums: [levels][n_sets] W_l, [n_sets] S, [n_sets] set sums
 // F: register-level type of the latency-bound launches; FB: of a reduce level with so many groups
 // (>= kBigLevel work items) that it is throughput-bound (G2: lane pairs lose there, 2.87 vs 2.36 ms
@@ -423,8 +436,29 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const Msm
   uint32_t count = p.half;
   char* run_cursor = scratch;
   char* w0 = scratch + p.red_run_total * kPt;
-  char* stage = w0 + uint64_t(p.n_sets) * ((p.half + kRedGroup - 1) / kRedGroup) * kPt;
+  char* stage = w0 + p.red_run_total * kPt;
   const size_t smem = (128 / L) * kPt;
+  // the sums of every level's w0 (-> W_l) and of the last level's runs (-> S) wait until all levels
+  // ran, then share one launch per stage
+  SumJobs first{}, second{};
+  auto add_sum = [&](const char* src, uint32_t n_in, char* dst) {
+    const uint32_t slices = msm_tail_slices(n_in);
+    const uint32_t j = first.n++;
+    first.in[j] = src;
+    first.count[j] = n_in;
+    first.slices[j] = slices;
+    first.first[j + 1] = first.first[j] + p.n_sets * slices;
+    first.out[j] = slices > 1 ? stage : dst;
+    if (slices > 1) {
+      const uint32_t k = second.n++;
+      second.in[k] = stage;
+      second.count[k] = slices;
+      second.slices[k] = 1;
+      second.first[k + 1] = second.first[k] + p.n_sets;
+      second.out[k] = dst;
+      stage += uint64_t(p.n_sets) * slices * kPt;
+    }
+  };
   uint32_t groups = 0;
   for (uint32_t l = 0; l < p.red_levels; l++) {
     groups = (count + kRedGroup - 1) / kRedGroup;
@@ -434,24 +468,17 @@ void msm_tail_t(const MsmPlan& p, const MsmBuffers& b, cudaStream_t s, const Msm
       msm_reduce_level_kernel<FB><<<(threads * FB::kLanes + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
     else
       msm_reduce_level_kernel<F><<<(threads * L + 127) / 128, 128, 0, s>>>(in, count, groups, p.n_sets, run_cursor, w0, last);
-    // W_l[set] = sum of this level's w0 (two-stage when there are many)
-    const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
-    char* wl_out = wl + uint64_t(l) * p.n_sets * kPt;
-    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, smem, s>>>(w0, groups, slices, slices > 1 ? stage : wl_out);
-    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, smem, s>>>(stage, slices, 1, wl_out);
-    count_launches(slices > 1 ? 3 : 2);
+    add_sum(w0, groups, wl + uint64_t(l) * p.n_sets * kPt);          // W_l[set] = sum of this level's w0
     in = run_cursor;
     run_cursor += uint64_t(threads) * kPt;
+    w0 += uint64_t(threads) * kPt;
     count = groups;
   }
-  // S[set] = sum of the runs of the last level
+  add_sum(in, groups, wl + uint64_t(p.red_levels) * p.n_sets * kPt);  // S[set] = sum of the runs of the last level
   char* s_tot = wl + uint64_t(p.red_levels) * p.n_sets * kPt;
-  {
-    const uint32_t slices = groups >= 4096 ? 64 : (groups >= 256 ? 8 : 1);
-    msm_window_sum_kernel<F><<<p.n_sets * slices, 128, smem, s>>>(in, groups, slices, slices > 1 ? stage : s_tot);
-    if (slices > 1) msm_window_sum_kernel<F><<<p.n_sets, 128, smem, s>>>(stage, slices, 1, s_tot);
-    count_launches(slices > 1 ? 3 : 2);   // + the Horner kernel below
-  }
+  msm_window_sum_kernel<F><<<first.first[first.n], 128, smem, s>>>(first);
+  if (second.n) msm_window_sum_kernel<F><<<second.first[second.n], 128, smem, s>>>(second);
+  count_launches(p.red_levels + (second.n ? 3 : 2));   // reduce levels + sums + the Horner kernel below
   MsmOutPtrs outs{};
   if (independent) outs = *independent;
   msm_horner_kernel<F><<<1, 128 * L, 0, s>>>(wl, s_tot, p.red_levels, p.n_sets, p.c,

@@ -63,8 +63,11 @@ __device__ __forceinline__ bool scalar_is_canonical(const uint32_t (&s)[9]) {
   return lt;
 }
 
-// calls f(key, val) for every non-zero digit of scalar i
-template <class Fn>
+// calls f(key, val) for every non-zero digit of scalar i.  C > 0 fixes the window width at compile
+// time: the loop unrolls, every window's word index and shift become immediates and the scalar's
+// limbs stay in registers (with a run-time width the limb array is indexed dynamically and lives in
+// local memory — the digit loop, not HBM, then bounds passes A and B).  C == 0 is the generic path.
+template <uint32_t C, class Fn>
 __device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ scalars, uint64_t i, const DigitCfg& d,
                                                uint32_t* flag, bool check, Fn f) {
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * i);
@@ -72,27 +75,35 @@ __device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ scal
   uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
   if (check && !scalar_is_canonical(s)) atomicOr(flag, 1u);
   uint32_t carry = 0;
-  for (uint32_t w = 0; w < d.nwin; w++) {
-    uint32_t bit = w * d.c;
-    uint32_t word = bit >> 5, sh = bit & 31;
-    uint32_t dg = 0;
-    if (word < 8) {
-      uint64_t two = (uint64_t(s[word + 1]) << 32) | s[word];
-      dg = uint32_t(two >> sh) & d.mask;
+  const uint32_t idx = d.idx_base + uint32_t(i);
+  if constexpr (C != 0) {
+    constexpr uint32_t kWin = (255 + C - 1) / C, kMask = (1u << C) - 1, kHalf = 1u << (C - 1);
+#pragma unroll
+    for (uint32_t w = 0; w < kWin; w++) {
+      const uint32_t bit = w * C, word = bit >> 5, sh = bit & 31;
+      uint32_t dg = (word < 8 ? __funnelshift_r(s[word], s[word + 1], sh) & kMask : 0u) + carry;
+      uint32_t neg = dg > kHalf;
+      uint32_t mag = neg ? (1u << C) - dg : dg;
+      carry = neg;
+      if (mag) f((d.one_set ? 0u : w * kHalf) + (mag - 1), (w * d.val_stride + idx) | (neg << 31));
     }
-    dg += carry;
-    uint32_t neg = dg > d.half;
-    uint32_t mag = neg ? (1u << d.c) - dg : dg;
-    carry = neg;
-    if (mag) {
-      uint32_t key = (d.one_set ? 0u : w * d.half) + (mag - 1);
-      uint32_t val = (w * d.val_stride + d.idx_base + uint32_t(i)) | (neg << 31);
-      f(key, val);
+  } else {
+    for (uint32_t w = 0; w < d.nwin; w++) {
+      uint32_t bit = w * d.c;
+      uint32_t word = bit >> 5, sh = bit & 31;
+      uint32_t dg = 0;
+      if (word < 8) dg = __funnelshift_r(s[word], s[word + 1], sh) & d.mask;
+      dg += carry;
+      uint32_t neg = dg > d.half;
+      uint32_t mag = neg ? (1u << d.c) - dg : dg;
+      carry = neg;
+      if (mag) f((d.one_set ? 0u : w * d.half) + (mag - 1), (w * d.val_stride + idx) | (neg << 31));
     }
   }
 }
 
 // ---------------------------------------------------------------- A: coarse histogram
+template <uint32_t C>
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
                                                                  DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
                                                                  uint32_t per_cta, uint32_t* __restrict__ coarse_hist,
@@ -103,7 +114,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t*
   const uint64_t first = uint64_t(blockIdx.x) * per_cta;
   const uint64_t last = first + per_cta < n ? first + per_cta : n;
   for (uint64_t i = first + threadIdx.x; i < last; i += blockDim.x)
-    for_each_digit(scalars, i, d, flag, true, [&](uint32_t key, uint32_t) { atomicAdd(&sm_cnt[key >> lo_bits], 1u); });
+    for_each_digit<C>(scalars, i, d, flag, true, [&](uint32_t key, uint32_t) { atomicAdd(&sm_cnt[key >> lo_bits], 1u); });
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < n_coarse; b += blockDim.x) {
     uint32_t v = sm_cnt[b];
@@ -157,22 +168,34 @@ __global__ void __launch_bounds__(1024) sort_plan_kernel(const uint32_t* __restr
   }
 }
 
-// exclusive scan of v[0..n) in shared memory by the whole CTA (n <= 4 * blockDim.x is typical);
-// `part` is blockDim.x words of scratch.  On return v[i] = sum of the old v[0..i).
+// exclusive scan of v[0..n) in shared memory by the whole CTA (blockDim.x a multiple of 32, <= 1024;
+// n <= 4 * blockDim.x is typical); `part` is >= 32 words of scratch.  On return v[i] = sum of the old
+// v[0..i).  Warp shuffles + one pass over the warp totals: three barriers, not two per doubling step.
 __device__ __forceinline__ void block_exclusive_scan(uint32_t* v, uint32_t n, uint32_t* part) {
-  const uint32_t t = threadIdx.x, T = blockDim.x, per = (n + T - 1) / T;
+  const uint32_t t = threadIdx.x, T = blockDim.x, per = (n + T - 1) / T, lane = t & 31, warp = t >> 5;
   const uint32_t lo = t * per, hi = lo + per < n ? lo + per : n;
   uint32_t sum = 0;
   for (uint32_t i = lo; i < hi; i++) sum += v[i];
-  part[t] = sum;
-  __syncthreads();
-  for (uint32_t o = 1; o < T; o <<= 1) {
-    uint32_t a = t >= o ? part[t - o] : 0;
-    __syncthreads();
-    part[t] += a;
-    __syncthreads();
+  uint32_t inc = sum;
+#pragma unroll
+  for (uint32_t o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
   }
-  uint32_t off = part[t] - sum;
+  if (lane == 31) part[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < (T >> 5) ? part[lane] : 0;
+    uint32_t winc = w;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += y;
+    }
+    part[lane] = winc - w;
+  }
+  __syncthreads();
+  uint32_t off = part[warp] + inc - sum;
   for (uint32_t i = lo; i < hi; i++) {
     uint32_t c = v[i];
     v[i] = off;
@@ -183,6 +206,7 @@ __device__ __forceinline__ void block_exclusive_scan(uint32_t* v, uint32_t n, ui
 
 // ---------------------------------------------------------------- B: scatter into coarse bins
 // dynamic shared memory: kCap staged entries | n_coarse run cursors | n_coarse (global base - local start)
+template <uint32_t C>
 __global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
                                                                      DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
                                                                      uint32_t per_cta, uint32_t* __restrict__ cursor,
@@ -198,7 +222,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint3
   const uint64_t first = uint64_t(blockIdx.x) * per_cta;
   const uint64_t last = first + per_cta < n ? first + per_cta : n;
   for (uint64_t i = first + t; i < last; i += blockDim.x)
-    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t) { atomicAdd(&run[key >> lo_bits], 1u); });
+    for_each_digit<C>(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t) { atomicAdd(&run[key >> lo_bits], 1u); });
   __syncthreads();
   // reserve this tile's run in every bin it touches, then turn the counts into local start offsets
   for (uint32_t b = t; b < n_coarse; b += blockDim.x) {
@@ -210,7 +234,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint3
   for (uint32_t b = t; b < n_coarse; b += blockDim.x) gbase[b] -= run[b];     // global pos = gbase[bin] + local index
   __syncthreads();
   for (uint64_t i = first + t; i < last; i += blockDim.x)
-    for_each_digit(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t val) {
+    for_each_digit<C>(scalars, i, d, nullptr, false, [&](uint32_t key, uint32_t val) {
       uint32_t pos = atomicAdd(&run[key >> lo_bits], 1u);
       sm_stage[pos] = make_uint2(key, val);
     });
@@ -223,6 +247,22 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint3
   }
 }
 
+// visits mid[s0 + i] for i in [0, cnt) with the whole CTA, four independent loads in flight per
+// thread before the dependent shared-memory atomics (these loops are latency-bound otherwise)
+template <class Fn>
+__device__ __forceinline__ void for_each_entry(const uint2* __restrict__ mid, uint32_t s0, uint32_t cnt, Fn f) {
+  const uint32_t t = threadIdx.x, T = blockDim.x;
+  for (uint32_t i = t; i < cnt; i += 4 * T) {
+    uint2 e[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++)
+      if (i + j * T < cnt) e[j] = mid[s0 + i + j * T];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++)
+      if (i + j * T < cnt) f(e[j]);
+  }
+}
+
 // ---------------------------------------------------------------- C1: fine histograms of oversized bins
 __global__ void __launch_bounds__(kSortThreads) sort_fine_hist_kernel(const uint2* __restrict__ mid,
                                                                       const uint32_t* __restrict__ coarse_off,
@@ -231,21 +271,40 @@ __global__ void __launch_bounds__(kSortThreads) sort_fine_hist_kernel(const uint
                                                                       const uint32_t* __restrict__ bin_multi,
                                                                       uint32_t lo_bits, uint32_t* __restrict__ fine) {
   __shared__ uint32_t cnt[kMaxFine];
-  for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
+  // a CTA takes a CONTIGUOUS range of work items: the segments of one bin are neighbours in the list,
+  // so the shared-memory histogram is flushed (with atomics: a bin can straddle two CTAs) only when
+  // the bin changes, not once per segment
+  const uint32_t total = *n_items, per = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t it0 = blockIdx.x * per, it1 = it0 + per < total ? it0 + per : total;
+  const uint32_t L = 1u << lo_bits, mask = L - 1;
+  uint32_t open_bin = 0xffffffffu;
+  for (uint32_t it = it0; it < it1; it++) {
     const uint2 w = items[it];
-    if (!bin_multi[w.x]) continue;
-    const uint32_t L = 1u << lo_bits, mask = L - 1;
-    for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) cnt[f] = 0;
-    __syncthreads();
+    if (w.x != open_bin) {
+      if (open_bin != 0xffffffffu) {
+        __syncthreads();
+        for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) {
+          uint32_t v = cnt[f];
+          if (v) atomicAdd(&fine[(uint64_t(open_bin) << lo_bits) + f], v);
+        }
+        open_bin = 0xffffffffu;
+      }
+      if (!bin_multi[w.x]) continue;
+      __syncthreads();
+      for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) cnt[f] = 0;
+      __syncthreads();
+      open_bin = w.x;
+    }
     const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
     const uint32_t s0 = b0 + w.y * (kCap / 2), s1 = s0 + kCap / 2 < b1 ? s0 + kCap / 2 : b1;
-    for (uint32_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) atomicAdd(&cnt[mid[i].x & mask], 1u);
+    for_each_entry(mid, s0, s1 - s0, [&](uint2 e) { atomicAdd(&cnt[e.x & mask], 1u); });
+  }
+  if (open_bin != 0xffffffffu) {
     __syncthreads();
     for (uint32_t f = threadIdx.x; f < L; f += blockDim.x) {
       uint32_t v = cnt[f];
-      if (v) atomicAdd(&fine[(uint64_t(w.x) << lo_bits) + f], v);
+      if (v) atomicAdd(&fine[(uint64_t(open_bin) << lo_bits) + f], v);
     }
-    __syncthreads();
   }
 }
 
@@ -302,7 +361,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
     __syncthreads();
     const uint32_t b0 = coarse_off[w.x], b1 = coarse_off[w.x + 1];
     const uint32_t s0 = b0 + w.y * kSeg, s1 = s0 + kSeg < b1 ? s0 + kSeg : b1, cnt = s1 - s0;
-    for (uint32_t i = t; i < cnt; i += blockDim.x) atomicAdd(&run[mid[s0 + i].x & mask], 1u);
+    for_each_entry(mid, s0, cnt, [&](uint2 e) { atomicAdd(&run[e.x & mask], 1u); });
     __syncthreads();
     if (bin_multi[w.x]) {
       // shared bin: reserve this segment's run in every fine bucket from the global cursors
@@ -319,10 +378,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
       for (uint32_t f = t; f < L; f += blockDim.x) gbase[f] = b0;
     }
     __syncthreads();
-    for (uint32_t i = t; i < cnt; i += blockDim.x) {
-      uint2 e = mid[s0 + i];
-      sorted[atomicAdd(&run[e.x & mask], 1u)] = e;
-    }
+    for_each_entry(mid, s0, cnt, [&](uint2 e) { sorted[atomicAdd(&run[e.x & mask], 1u)] = e; });
     __syncthreads();
     for (uint32_t i = t; i < cnt; i += blockDim.x) {
       uint2 e = sorted[i];
@@ -375,7 +431,13 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
   cudaGetDevice(&dev);
   std::call_once(configured[dev & 63], [] {
     cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kSeg) * 8 + kMaxFine * 8));
-    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kCap) * 8 + kMaxCoarse * 8));
+    const int scatter_max = int(size_t(kCap) * 8 + kMaxCoarse * 8);
+    cudaFuncSetAttribute(sort_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
+    cudaFuncSetAttribute(sort_scatter_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
+    cudaFuncSetAttribute(sort_scatter_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
+    cudaFuncSetAttribute(sort_scatter_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
+    cudaFuncSetAttribute(sort_scatter_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
+    cudaFuncSetAttribute(sort_scatter_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
   });
   if (b.ev) cudaEventRecord(b.ev[0], st);
   char* sc = reinterpret_cast<char*>(b.sort_temp);
@@ -400,13 +462,28 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
   // pass A: any tiling does; pass B: a tile's entries (<= windows per scalar) must fit the staging area
   const uint32_t per_a = 4096, per_b = kCap / p.nwin;
   const uint32_t tiles_a = uint32_t((n + per_a - 1) / per_a), tiles_b = uint32_t((n + per_b - 1) / per_b);
-  sort_hist_kernel<<<tiles_a ? tiles_a : 1, kSortThreads, size_t(s.n_coarse) * 4, st>>>(
-      reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits, s.n_coarse, per_a, coarse_hist, b.flag);
-  sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items, bin_multi);
-  sort_scatter_kernel<<<tiles_b ? tiles_b : 1, kPlaceThreads, scatter_smem, st>>>(
-      reinterpret_cast<const uint32_t*>(d_scalars), n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);
+  const uint32_t* sc32 = reinterpret_cast<const uint32_t*>(d_scalars);
+  // the widths msm_auto_window picks get unrolled digit loops; any other width takes the generic kernels
+#define ZKB_SORT_AB(C)                                                                                              \
+  do {                                                                                                              \
+    sort_hist_kernel<C><<<tiles_a ? tiles_a : 1, kSortThreads, size_t(s.n_coarse) * 4, st>>>(                       \
+        sc32, n, d, s.lo_bits, s.n_coarse, per_a, coarse_hist, b.flag);                                             \
+    sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items,    \
+                                         bin_multi);                                                                \
+    sort_scatter_kernel<C><<<tiles_b ? tiles_b : 1, kPlaceThreads, scatter_smem, st>>>(                             \
+        sc32, n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);                                                     \
+  } while (0)
+  switch (p.c) {
+    case 15: ZKB_SORT_AB(15); break;
+    case 17: ZKB_SORT_AB(17); break;
+    case 20: ZKB_SORT_AB(20); break;
+    case 22: ZKB_SORT_AB(22); break;
+    case 24: ZKB_SORT_AB(24); break;
+    default: ZKB_SORT_AB(0); break;
+  }
+#undef ZKB_SORT_AB
   if (b.ev) cudaEventRecord(b.ev[1], st);
-  const uint32_t grid_c = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;
+  const uint32_t grid_c = uint32_t(sm_count) * 4 < s.max_items ? uint32_t(sm_count) * 4 : s.max_items;
   sort_fine_hist_kernel<<<grid_c, kSortThreads, 0, st>>>(mid, coarse_off, items, n_items, bin_multi, s.lo_bits, fine);
   sort_fine_scan_kernel<<<s.n_coarse < 296 ? s.n_coarse : 296, 1024, 0, st>>>(coarse_off, bin_multi, s.n_coarse, s.lo_bits, fine);
   const uint32_t grid_p = uint32_t(sm_count) * 2 < s.max_items ? uint32_t(sm_count) * 2 : s.max_items;

@@ -8,12 +8,13 @@ import eigen_zeth_b200 as z
 import oracle_b as ob
 
 sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "19,22,24").split(",")]
+windows = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]   # 0 = the library's choice
 ctx = z.Context(0)
 out = []
-for log_n in sizes:
+for log_n, window in [(a, b) for a in sizes for b in windows]:
     n = 1 << log_n
     bases = ctx.synthetic_bases(n, 0x5EED0001)
-    bases.precompute(0)
+    bases.precompute(window)
     res = torch.zeros(64, dtype=torch.uint8, device="cuda")
     uni = ob.random_scalars(n, 0x5EED0000 + log_n)
     inputs = {"uniform": uni, "zero_one": b"".join((i & 1).to_bytes(32, "little") for i in range(1 << 16)) * (n >> 16),
