@@ -623,6 +623,7 @@ __global__ void field_batch_kernel(int op, const F* a, const F* b, F* out, uint6
     case 6: r = x.sqr_dedicated(); break;
     case 7: r = F::mul_add_mul(x, y, x + y, x - y); break;   // fused dual product, operands up to 2p
     case 8: r = F::mul_sub_mul(x, y, x + y, x - y); break;
+    case 9: r = x.inverse_fermat(); break;
     default: r = x.neg(); break;
   }
   r.from_mont().store(out + i);
@@ -1296,7 +1297,7 @@ int zkb_msm_last_timings(zkb_ctx* ctx, float ms_out[5]) {
 int zkb_field_batch_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
                        uint8_t* out, uint64_t n) {
   ZKB_ENTER(ctx);
-  if (!a || !out || op < 0 || op > 8 || field < 0 || field > 1) return set_error(ctx, ZKB_EINVAL, "bad argument");
+  if (!a || !out || op < 0 || op > 9 || field < 0 || field > 1) return set_error(ctx, ZKB_EINVAL, "bad argument");
   if (op <= 2 && !b) return set_error(ctx, ZKB_EINVAL, "binary op needs b");
   if (!n) return ZKB_OK;
   ZKB_CUDA(ctx, ctx->io_a.ensure(n * 32));

@@ -10,15 +10,18 @@
 //   P  plan        one CTA: exclusive scan of the coarse histogram (= where each bin starts in the
 //                  output AND in the intermediate array), m_valid, and the work list of pass C:
 //                  one item per bin, or several per bin when a bin is larger than a CTA can hold.
-//   B  scatter     a tile = the <= kCap entries of ~kCap / windows scalars.  The tile is counting-sorted
+//   B  scatter     a tile = the <= kTile entries of ~kTile / windows scalars.  The tile is counting-sorted
 //                  by coarse bin INSIDE shared memory (count, scan, place), room is reserved per
 //                  (tile, bin) with one global atomic, and the staged tile is written out linearly:
-//                  neighbouring threads write neighbouring entries of one run (~10 entries = 80 B per
+//                  neighbouring threads write neighbouring entries of one run (~5 entries = 40 B per
 //                  bin per tile with 2^11 bins), so the stores coalesce and every run is written at
-//                  once.  (A first version scattered straight from registers: each of the ~450
-//                  resident tiles then kept 16 K half-written lines open, 900 MB of them — far beyond
-//                  the 126 MB L2 — and the pass took 7 ms at 2^24 points instead of < 1 ms.)
-//   C  bucketize   one CTA per work item loads its segment (<= kCap entries, 8 B each) into shared
+//                  once.  Two tiles are resident per SM so that one tile's barriers hide under the
+//                  other's work (measured at 2^24: 10 K-entry tiles, two per SM, 0.98 ms; 20 K-entry
+//                  tiles, one per SM, 1.09 ms; 512-thread CTAs with 4-8 K tiles, 1.3-1.4 ms).  (A first
+//                  version scattered straight from registers: each of the ~450 resident tiles then kept
+//                  16 K half-written lines open, 900 MB of them — far beyond the 126 MB L2 — and the
+//                  pass took 7 ms at 2^24 points.)
+//   C  bucketize   one CTA per work item loads its segment (<= kSeg entries, 8 B each) into shared
 //                  memory, counting-sorts it by fine bucket (key & (2^lo_bits - 1)) in shared memory
 //                  and writes it out linearly to the bucket's final position.  A bin that fits one
 //                  segment is the CTA's private output region (offsets from a local scan).  Larger
@@ -40,7 +43,8 @@ namespace zkb {
 
 constexpr uint32_t kSortThreads = 512;
 constexpr uint32_t kPlaceThreads = 1024;
-constexpr uint32_t kCap = 20480;            // entries a pass-B tile / pass-C segment holds in shared memory (160 KB)
+constexpr uint32_t kCap = 20480;            // 2 * kSeg: a coarse bin up to kCap / 6 entries on average stays private
+constexpr uint32_t kTile = kCap / 2;        // entries of a pass-B tile (80 KB staged + 16 KB bin tables: two CTAs per SM)
 constexpr uint32_t kMaxCoarse = 2048;       // coarse bins: ~10 entries per (tile, bin) run
 constexpr uint32_t kMaxFine = 4096;         // fine buckets per coarse bin
 
@@ -207,14 +211,14 @@ __device__ __forceinline__ void block_exclusive_scan(uint32_t* v, uint32_t n, ui
 // ---------------------------------------------------------------- B: scatter into coarse bins
 // dynamic shared memory: kCap staged entries | n_coarse run cursors | n_coarse (global base - local start)
 template <uint32_t C>
-__global__ void __launch_bounds__(kPlaceThreads) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
+__global__ void __launch_bounds__(kPlaceThreads, 2) sort_scatter_kernel(const uint32_t* __restrict__ scalars, uint64_t n,
                                                                      DigitCfg d, uint32_t lo_bits, uint32_t n_coarse,
                                                                      uint32_t per_cta, uint32_t* __restrict__ cursor,
                                                                      uint2* __restrict__ mid) {
   extern __shared__ uint2 sm_stage[];
-  uint32_t* run = reinterpret_cast<uint32_t*>(sm_stage + kCap);
+  uint32_t* run = reinterpret_cast<uint32_t*>(sm_stage + kTile);
   uint32_t* gbase = run + n_coarse;
-  __shared__ uint32_t part[kPlaceThreads];
+  __shared__ uint32_t part[32];
   __shared__ uint32_t total;
   const uint32_t t = threadIdx.x;
   for (uint32_t b = t; b < n_coarse; b += blockDim.x) run[b] = 0;
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(1024) sort_fine_scan_kernel(const uint32_t* __
 // start).  The segment is read twice from global memory (count, then place: the second read hits L2)
 // rather than staged, so that two CTAs fit on an SM.
 constexpr uint32_t kSeg = kCap / 2;
-__global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* __restrict__ mid,
+__global__ void __launch_bounds__(kPlaceThreads, 2) sort_place_kernel(const uint2* __restrict__ mid,
                                                                   const uint32_t* __restrict__ coarse_off,
                                                                   const uint2* __restrict__ items,
                                                                   const uint32_t* __restrict__ n_items,
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kPlaceThreads) sort_place_kernel(const uint2* 
   extern __shared__ uint2 sorted[];
   uint32_t* run = reinterpret_cast<uint32_t*>(sorted + kSeg);
   uint32_t* gbase = run + (1u << lo_bits);
-  __shared__ uint32_t part[kPlaceThreads];
+  __shared__ uint32_t part[32];
   for (uint32_t it = blockIdx.x; it < *n_items; it += gridDim.x) {
     const uint2 w = items[it];
     const uint32_t L = 1u << lo_bits, mask = L - 1, t = threadIdx.x;
@@ -424,14 +428,14 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
                                 uint32_t idx_base, int sm_count, cudaStream_t st) {
   const SortPlan s = msm_sort_plan(p);
   const size_t place_smem = size_t(kSeg) * 8 + (size_t(8) << s.lo_bits);
-  const size_t scatter_smem = size_t(kCap) * 8 + size_t(8) * s.n_coarse;
+  const size_t scatter_smem = size_t(kTile) * 8 + size_t(8) * s.n_coarse;
   // opt-in to large dynamic shared memory, once per device of this process
   static std::once_flag configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(configured[dev & 63], [] {
     cudaFuncSetAttribute(sort_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(kSeg) * 8 + kMaxFine * 8));
-    const int scatter_max = int(size_t(kCap) * 8 + kMaxCoarse * 8);
+    const int scatter_max = int(size_t(kTile) * 8 + kMaxCoarse * 8);
     cudaFuncSetAttribute(sort_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
     cudaFuncSetAttribute(sort_scatter_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
     cudaFuncSetAttribute(sort_scatter_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_max);
@@ -460,7 +464,7 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
   d.idx_base = idx_base;
   d.one_set = p.val_stride != 0;
   // pass A: any tiling does; pass B: a tile's entries (<= windows per scalar) must fit the staging area
-  const uint32_t per_a = 4096, per_b = kCap / p.nwin;
+  const uint32_t per_a = 4096, per_b = kTile / p.nwin;
   const uint32_t tiles_a = uint32_t((n + per_a - 1) / per_a), tiles_b = uint32_t((n + per_b - 1) / per_b);
   const uint32_t* sc32 = reinterpret_cast<const uint32_t*>(d_scalars);
   // the widths msm_auto_window picks get unrolled digit loops; any other width takes the generic kernels
@@ -471,7 +475,7 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
     sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items,    \
                                          bin_multi);                                                                \
     sort_scatter_kernel<C><<<tiles_b ? tiles_b : 1, kPlaceThreads, scatter_smem, st>>>(                             \
-        sc32, n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);                                                     \
+        sc32, n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);                                                   \
   } while (0)
   switch (p.c) {
     case 15: ZKB_SORT_AB(15); break;

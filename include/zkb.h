@@ -331,7 +331,8 @@ int zkb_wtns_read(const uint8_t* file, uint64_t len, uint8_t* witness_out);
 /* element-wise field ops on host arrays of canonical elements, executed by the device field
  * library: field 0 = Fq, 1 = Fr; op 0 add, 1 sub, 2 mul, 3 sqr, 4 inverse, 5 neg,
  * 6 sqr through the dedicated (experimental, not used by the hot kernels) squaring routine,
- * 7 / 8 the fused dual product a*b + (a+b)*(a-b) / a*b - (a+b)*(a-b) (one shared reduction) */
+ * 7 / 8 the fused dual product a*b + (a+b)*(a-b) / a*b - (a+b)*(a-b) (one shared reduction),
+ * 9 inverse by Fermat exponentiation (op 4 is the binary extended Euclid the kernels use) */
 int zkb_field_batch_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
                        uint8_t* out, uint64_t n);
 /* curve ops through the device XYZZ library: group 0 = G1, 1 = G2;

@@ -10,7 +10,9 @@ OPS = {0: lambda a, b, p: (a + b) % p, 1: lambda a, b, p: (a - b) % p, 2: lambda
        3: lambda a, b, p: a * a % p, 4: lambda a, b, p: pow(a, p - 2, p), 5: lambda a, b, p: (-a) % p,
        6: lambda a, b, p: a * a % p,
        # fused dual products (mont_mul2: two products, one Montgomery reduction)
-       7: lambda a, b, p: (a * b + (a + b) * (a - b)) % p, 8: lambda a, b, p: (a * b - (a + b) * (a - b)) % p}
+       7: lambda a, b, p: (a * b + (a + b) * (a - b)) % p, 8: lambda a, b, p: (a * b - (a + b) * (a - b)) % p,
+       # op 4 = binary extended Euclid (what the kernels call), op 9 = Fermat exponentiation
+       9: lambda a, b, p: pow(a, p - 2, p)}
 
 
 @pytest.mark.parametrize("field", [0, 1])
