@@ -475,7 +475,7 @@ void msm_digits_and_bucket_sort(const MsmPlan& p, const MsmBuffers& b, const voi
     sort_plan_kernel<<<1, 1024, 0, st>>>(coarse_hist, s.n_coarse, coarse_off, cursor, b.m_valid, items, n_items,    \
                                          bin_multi);                                                                \
     sort_scatter_kernel<C><<<tiles_b ? tiles_b : 1, kPlaceThreads, scatter_smem, st>>>(                             \
-        sc32, n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);                                                   \
+        sc32, n, d, s.lo_bits, s.n_coarse, per_b, cursor, mid);                                                     \
   } while (0)
   switch (p.c) {
     case 15: ZKB_SORT_AB(15); break;
