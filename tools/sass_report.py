@@ -10,10 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "eigen-zeth_b200", "libzkb.so")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 KERNELS = [("msm_accumulate_l1_kernel<Fq>", r"msm_accumulate_l1_kernelINS_2FpINS_8FqParams"),
-           ("msm_accumulate_l1_kernel<Fq2>", r"msm_accumulate_l1_kernelINS_3Fq2E"),
+           ("msm_accumulate_l1_kernel<Fq2>", r"msm_accumulate_l1_kernelINS_4Fq2TILb0E"),
            ("msm_accumulate_l1_kernel<Fq2L>", r"msm_accumulate_l1_kernelINS_4Fq2LE"),
            ("ntt_pass_kernel<false>", r"ntt_pass_kernelILb0E"),
            ("ntt_pass_kernel<true>", r"ntt_pass_kernelILb1E"),
+           ("sort_scatter_kernel<22>", r"sort_scatter_kernelILj22E"),
+           ("sort_place_kernel", r"sort_place_kernel"),
+           ("msm_reduce_level_kernel<Fq>", r"msm_reduce_level_kernelINS_2FpINS_8FqParams"),
            ("imad_chain_kernel", r"imad_chain_kernel"),
            ("montmul_chain_kernel", r"montmul_chain_kernel")]
 OPS = ["IMAD.WIDE", "IMAD.HI", "IMAD", "IADD3", "LOP3", "SEL", "SHF", "SHFL", "LDG", "STG", "LDS", "STS", "LDL", "STL",
