@@ -4,9 +4,11 @@ The reference never sees a circuit: its prover is an external service (src/prove
 and the tree holds no R1CS, witness or key.  A deployment that swaps that service for this backend
 brings its circuit as the iden3 binary files circom writes:
   * `.r1cs`  — constraint system  -> the three CSR matrices of `zkb_pk_desc`;
-  * `.wtns`  — witness            -> the `witness` argument of `zkb_groth16_prove`.
+  * `.wtns`  — witness            -> the `witness` argument of `zkb_groth16_prove`;
+  * `.zkey`  — snarkjs / rapidsnark Groth16 proving key -> a complete `zkb_pk_desc` with
+    `h_basis = 1` (matrices A and B, the five queries, the fixed points) plus the verifying key.
 Reading is done by libzkb.so (csrc/circom_io.cpp: zkb_r1cs_inspect / zkb_r1cs_read /
-zkb_wtns_inspect / zkb_wtns_read) so a Rust or C++ host gets the same parser; this module is the
+zkb_wtns_inspect / zkb_wtns_read / zkb_zkey_inspect / zkb_zkey_read) so a Rust or C++ host gets the same parser; this module is the
 ctypes face of it plus writers (export of the synthetic benchmark circuit, test fixtures).
 """
 from __future__ import annotations
@@ -71,6 +73,67 @@ def read_wtns(data: bytes) -> bytes:
     if rc:
         raise zkb.ZkbError(rc, "witness holds a non-canonical value or wire 0 is not 1")
     return out.raw[:32 * n.value]
+
+
+@dataclass
+class Zkey:
+    n_vars: int
+    n_public: int
+    log_n: int
+    n_rows: int             # rows of A / B present in the key (constraints + the n_public + 1 input rows)
+    matrices: list          # two (row_ptr list[int], col list[int], coeff bytes): A, B
+    fixed: dict             # alpha_g1, beta_g1, delta_g1 (64 B), beta_g2, gamma_g2, delta_g2 (128 B)
+    ic: bytes               # 64 * (n_public + 1)
+    queries: dict           # a_query, b_g1_query, b_g2_query, l_query (the key's C section), h_query
+
+    def vk_bytes(self) -> bytes:
+        """the verifying key in the library's layout (one public input: ZKB_VK_BYTES = 576)"""
+        f = self.fixed
+        return f["alpha_g1"] + f["beta_g2"] + f["gamma_g2"] + f["delta_g2"] + self.ic
+
+
+def read_zkey(data: bytes) -> Zkey:
+    from . import lib as zkb
+    lib = zkb.load_library()
+    info = zkb.ZkeyInfo()
+    rc = lib.zkb_zkey_inspect(data, len(data), C.byref(info))
+    if rc:
+        raise zkb.ZkbError(rc, "not a BN254 Groth16 .zkey (magic, version, protocol, primes, section sizes or an index out of range)")
+    m, npub, n = info.n_vars, info.n_public, 1 << info.log_n
+    d = zkb.ZkeyData()
+    keep = {}
+
+    def buf(name, size):
+        keep[name] = C.create_string_buffer(max(1, size))
+        return C.cast(keep[name], C.c_void_p)
+
+    row_ptr = [(C.c_uint32 * (info.n_rows + 1))() for _ in range(2)]
+    col = [(C.c_uint32 * max(1, info.nnz[k]))() for k in range(2)]
+    for k in range(2):
+        d.row_ptr[k] = C.cast(row_ptr[k], C.c_void_p)
+        d.col[k] = C.cast(col[k], C.c_void_p)
+        d.coeff[k] = buf("coeff%d" % k, 32 * info.nnz[k])
+    sizes = {"alpha_g1": 64, "beta_g1": 64, "delta_g1": 64, "beta_g2": 128, "gamma_g2": 128, "delta_g2": 128,
+             "ic": 64 * (npub + 1), "a_query": 64 * m, "b_g1_query": 64 * m, "b_g2_query": 128 * m,
+             "c_query": 64 * (m - npub - 1), "h_query": 64 * n}
+    for name, size in sizes.items():
+        setattr(d, name, buf(name, size))
+    rc = lib.zkb_zkey_read(data, len(data), C.byref(d))
+    if rc:
+        raise zkb.ZkbError(rc, "zkb_zkey_read failed (a coordinate or coefficient is not reduced)")
+    raw = lambda name: keep[name].raw[:sizes[name]]
+    mats = [(list(row_ptr[k]), list(col[k])[:info.nnz[k]], keep["coeff%d" % k].raw[:32 * info.nnz[k]]) for k in range(2)]
+    fixed = {k: raw(k) for k in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "gamma_g2", "delta_g2")}
+    queries = {"a_query": raw("a_query"), "b_g1_query": raw("b_g1_query"), "b_g2_query": raw("b_g2_query"),
+               "l_query": raw("c_query"), "h_query": raw("h_query")}
+    return Zkey(m, npub, info.log_n, info.n_rows, mats, fixed, raw("ic"), queries)
+
+
+def load_zkey(ctx, data: bytes):
+    """.zkey bytes -> a resident ProvingKey on `ctx` (zkb_pk_load with h_basis = 1)"""
+    zk = read_zkey(data)
+    fixed = {k: zk.fixed[k] for k in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2")}
+    return ctx.pk_load(zk.log_n, zk.n_vars, zk.n_public, zk.matrices, zk.queries, fixed, vk=zk.vk_bytes(), h_basis=1), zk
 
 
 # ---- writers -------------------------------------------------------------------------------------

@@ -12,7 +12,17 @@
 //   .wtns  1  := n8:u32 prime[n8] n_witness:u32
 //          2  := n_witness x value[n8]
 //
-// All integers little-endian; coefficients and values are canonical (non-Montgomery) integers.
+//   .zkey  1  := protocol:u32 (1 = groth16)
+//          2  := n8q:u32 q[n8q] n8r:u32 r[n8r] n_vars:u32 n_public:u32 domain_size:u32
+//                alpha_g1 beta_g1 beta_g2 gamma_g2 delta_g1 delta_g2
+//          3  := IC (n_public + 1 G1)      4 := count:u32 (matrix:u32 row:u32 signal:u32 value[n8r])*
+//          5..9 := A (n_vars G1), B1 (n_vars G1), B2 (n_vars G2), C (n_vars - n_public - 1 G1),
+//                H (domain_size G1);   10 := contributions (not read)
+//          points: affine coordinates as Montgomery-form integers (G2: c0 then c1), all-zero =
+//          infinity; coefficient values: coefficient * 2^512 mod r.  The test tree holds a writer
+//          for this layout; it is not pinned against a snarkjs-written file (none in this image).
+//
+// All integers little-endian; .r1cs / .wtns coefficients and values are canonical (non-Montgomery) integers.
 // Wire 0 is the constant 1, followed by public outputs, public inputs, private inputs — the
 // z = (1, public..., private...) order zkb_pk_desc uses, so n_public = n_pub_out + n_pub_in.
 // Host code only; no allocation (two-pass: *_inspect sizes the caller's buffers, *_read fills them).
@@ -20,6 +30,7 @@
 #include <cstring>
 
 #include "../../include/zkb.h"
+#include "host_ff.hpp"
 
 namespace {
 
@@ -209,5 +220,146 @@ extern "C" int zkb_wtns_read(const uint8_t* file, uint64_t len, uint8_t* witness
   for (int i = 1; i < 32; i++)
     if (s[2].p[i]) return ZKB_EINVAL;
   std::memcpy(witness_out, s[2].p, uint64_t(n) * 32);
+  return ZKB_OK;
+}
+
+// ---------------------------------------------------------------- .zkey (snarkjs Groth16 proving key)
+namespace {
+
+using zkb::host::HFq;
+using zkb::host::HFr;
+
+// BN254 base field modulus q, little-endian bytes
+const uint8_t kFqModulus[32] = {0x47, 0xfd, 0x7c, 0xd8, 0x16, 0x8c, 0x20, 0x3c, 0x8d, 0xca, 0x71,
+                                0x68, 0x91, 0x6a, 0x81, 0x97, 0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45,
+                                0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+struct ZkeyHeader {
+  uint32_t n_vars, n_public, domain, log_n;
+  const uint8_t* fixed;   // alpha_g1 beta_g1 beta_g2 gamma_g2 delta_g1 delta_g2 (64 64 128 128 64 128)
+};
+
+bool zkey_header(const Section* s, ZkeyHeader* h) {
+  if (!s[1].p || !s[2].p) return false;
+  Cursor c1{s[1].p, s[1].p + s[1].size};
+  if (c1.u32() != 1 || !c1.ok) return false;                       // groth16
+  Cursor c{s[2].p, s[2].p + s[2].size};
+  uint32_t n8q = c.u32();
+  const uint8_t* q = c.bytes(32);
+  uint32_t n8r = c.u32();
+  const uint8_t* r = c.bytes(32);
+  if (!c.ok || n8q != 32 || n8r != 32 || std::memcmp(q, kFqModulus, 32) || std::memcmp(r, kFrModulus, 32))
+    return false;
+  h->n_vars = c.u32();
+  h->n_public = c.u32();
+  h->domain = c.u32();
+  h->fixed = c.bytes(64 + 64 + 128 + 128 + 64 + 128);
+  if (!c.ok || c.p != c.end) return false;
+  if (h->domain < 2 || (h->domain & (h->domain - 1)) || h->n_vars == 0 || h->n_public >= h->n_vars) return false;
+  h->log_n = 0;
+  while ((1u << h->log_n) < h->domain) h->log_n++;
+  // section sizes must agree with the header
+  const uint64_t m = h->n_vars, np = uint64_t(h->n_public) + 1;
+  return s[3].p && s[3].size == 64 * np && s[4].p && s[4].size >= 4 && s[5].p && s[5].size == 64 * m &&
+         s[6].p && s[6].size == 64 * m && s[7].p && s[7].size == 128 * m && (s[8].p || m == np) &&
+         s[8].size == 64 * (m - np) && s[9].p && s[9].size == 64ull * h->domain;
+}
+
+// count coordinates of 32 bytes each, Montgomery form -> canonical; false if one is not reduced
+bool coords_from_mont(const uint8_t* in, uint64_t count, uint8_t* out) {
+  for (uint64_t i = 0; i < count; i++) {
+    HFq a;
+    std::memcpy(a.l, in + 32 * i, 32);
+    if (!HFq::lt_mod(a.l)) return false;
+    a = a.from_mont();
+    std::memcpy(out + 32 * i, a.l, 32);
+  }
+  return true;
+}
+
+// walks the coefficient section.  Pass 1 (col == nullptr): validates and counts per (matrix, row)
+// into row_ptr[k][row + 1] when row_ptr is given, else only nnz / n_rows.  Pass 2: fills col / coeff
+// using row_ptr[k][row] as the running cursor of the row.
+bool zkey_coeffs(const Section& s, const ZkeyHeader& h, uint64_t nnz[2], uint32_t* n_rows,
+                 uint32_t* const row_ptr[2], uint32_t* const col[2], uint8_t* const coeff[2]) {
+  Cursor c{s.p, s.p + s.size};
+  const uint32_t count = c.u32();
+  if (!c.ok || s.size != 4 + 44ull * count) return false;
+  uint64_t cnt[2] = {0, 0};
+  uint32_t rows = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    const uint32_t mat = c.u32(), row = c.u32(), sig = c.u32();
+    const uint8_t* v = c.bytes(32);
+    if (!c.ok || mat > 1 || row >= h.domain || sig >= h.n_vars) return false;
+    if (row + 1 > rows) rows = row + 1;
+    cnt[mat]++;
+    if (col) {
+      HFr a;
+      std::memcpy(a.l, v, 32);
+      if (!HFr::lt_mod(a.l)) return false;
+      a = a.from_mont().from_mont();                                // value = coefficient * R^2
+      const uint32_t pos = row_ptr[mat][row]++;
+      col[mat][pos] = sig;
+      std::memcpy(coeff[mat] + 32ull * pos, a.l, 32);
+    } else if (row_ptr) {
+      row_ptr[mat][row + 1]++;
+    }
+  }
+  if (nnz) { nnz[0] = cnt[0]; nnz[1] = cnt[1]; }
+  if (n_rows) *n_rows = rows;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int zkb_zkey_inspect(const uint8_t* file, uint64_t len, zkb_zkey_info* out) {
+  if (!out) return ZKB_EINVAL;
+  Section s[11];
+  ZkeyHeader h;
+  if (!find_sections(file, len, "zkey", 1, 1, s, 10) || !zkey_header(s, &h)) return ZKB_EINVAL;
+  uint64_t nnz[2];
+  uint32_t rows;
+  if (!zkey_coeffs(s[4], h, nnz, &rows, nullptr, nullptr, nullptr)) return ZKB_EINVAL;
+  out->n_vars = h.n_vars;
+  out->n_public = h.n_public;
+  out->log_n = h.log_n;
+  out->n_rows = rows;
+  out->nnz[0] = nnz[0];
+  out->nnz[1] = nnz[1];
+  return ZKB_OK;
+}
+
+extern "C" int zkb_zkey_read(const uint8_t* file, uint64_t len, const zkb_zkey_data* d) {
+  if (!d) return ZKB_EINVAL;
+  Section s[11];
+  ZkeyHeader h;
+  if (!find_sections(file, len, "zkey", 1, 1, s, 10) || !zkey_header(s, &h)) return ZKB_EINVAL;
+  uint64_t nnz[2];
+  uint32_t rows;
+  if (!zkey_coeffs(s[4], h, nnz, &rows, nullptr, nullptr, nullptr)) return ZKB_EINVAL;
+  if (d->row_ptr[0] || d->row_ptr[1]) {
+    // the matrices come together (one walk fills both)
+    for (int k = 0; k < 2; k++)
+      if (!d->row_ptr[k] || (nnz[k] && (!d->col[k] || !d->coeff[k]))) return ZKB_EINVAL;
+    for (int k = 0; k < 2; k++) std::memset(d->row_ptr[k], 0, 4ull * (rows + 1));
+    if (!zkey_coeffs(s[4], h, nullptr, nullptr, d->row_ptr, nullptr, nullptr)) return ZKB_EINVAL;
+    for (int k = 0; k < 2; k++)                    // counts at [row + 1] -> row starts at [row]
+      for (uint32_t r = 0; r < rows; r++) d->row_ptr[k][r + 1] += d->row_ptr[k][r];
+    if (!zkey_coeffs(s[4], h, nullptr, nullptr, d->row_ptr, d->col, d->coeff)) return ZKB_EINVAL;
+    for (int k = 0; k < 2; k++) {                  // the cursors ended at the next row's start: shift back
+      for (uint32_t r = rows; r > 0; r--) d->row_ptr[k][r] = d->row_ptr[k][r - 1];
+      d->row_ptr[k][0] = 0;
+    }
+  }
+  const uint8_t* f = h.fixed;
+  struct Item { uint8_t* out; const uint8_t* in; uint64_t coords; };
+  const uint64_t m = h.n_vars, np = uint64_t(h.n_public) + 1;
+  const Item items[] = {{d->alpha_g1, f, 2},       {d->beta_g1, f + 64, 2},   {d->beta_g2, f + 128, 4},
+                        {d->gamma_g2, f + 256, 4}, {d->delta_g1, f + 384, 2}, {d->delta_g2, f + 448, 4},
+                        {d->ic, s[3].p, 2 * np},   {d->a_query, s[5].p, 2 * m}, {d->b_g1_query, s[6].p, 2 * m},
+                        {d->b_g2_query, s[7].p, 4 * m}, {d->c_query, s[8].p, 2 * (m - np)},
+                        {d->h_query, s[9].p, 2ull * h.domain}};
+  for (const Item& it : items)
+    if (it.out && it.coords && !coords_from_mont(it.in, it.coords, it.out)) return ZKB_EINVAL;
   return ZKB_OK;
 }

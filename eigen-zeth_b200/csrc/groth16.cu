@@ -46,6 +46,10 @@ struct zkb_pk {
   uint32_t n_inst = 2;       // instance variables incl. the constant one: z[0] = 1, z[1..n_inst)
   uint32_t rank = 0, world = 1;
   uint32_t h_low_bits = 0;   // != 0: h_query is held in "layout d" of the four-step NTT (csrc/dist.cu)
+  // 1: snarkjs key (zkb_pk_desc.h_basis): h_query = L_{2i+1}(tau)/delta over the size-2n domain, n points;
+  // A holds the input rows explicitly, there is no C matrix, d_shift = w_2n^i (Montgomery, n entries)
+  uint32_t h_basis = 0;
+  void* d_shift = nullptr;
   uint64_t qfirst[5] = {0, 0, 0, 0, 0}, qcount[5] = {0, 0, 0, 0, 0};
   // the prove entry points write the key's work vectors (d_a..d_zm, d_results, d_proof) behind a
   // const zkb_pk*: one prove at a time per key, whatever context it is called through
@@ -106,6 +110,19 @@ __global__ void qap_pointwise_kernel(Fr* a, const Fr* b, const Fr* c, uint64_t n
   uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   (Fr::load(a + i) * Fr::load(b + i) - Fr::load(c + i)).store(a + i);
+}
+
+// snarkjs keys: c[i] = a[i] * b[i] on the domain (no C matrix), and the H scalars
+// a[i] = a[i] * b[i] - c[i] on the odd coset, stored as canonical integers for the MSM
+__global__ void qap_product_kernel(const Fr* a, const Fr* b, Fr* c, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  (Fr::load(a + i) * Fr::load(b + i)).store(c + i);
+}
+__global__ void qap_pointwise_canonical_kernel(Fr* a, const Fr* b, const Fr* c, uint64_t n) {
+  uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  (Fr::load(a + i) * Fr::load(b + i) - Fr::load(c + i)).from_mont().store(a + i);
 }
 
 template <class F>
@@ -316,7 +333,7 @@ void zkb_pk_free(zkb_pk* pk) {
   zkb_bases_free(pk->l_query);
   zkb_bases_free(pk->h_query);
   void* ptrs[] = {pk->d_fixed, pk->d_coeff_table, pk->d_a, pk->d_b, pk->d_c, pk->d_z, pk->d_zm,
-                  pk->d_results, pk->d_proof};
+                  pk->d_results, pk->d_proof, pk->d_shift};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 3; k++) {
     if (pk->d_row_ptr[k]) cudaFree(pk->d_row_ptr[k]);
@@ -597,10 +614,13 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
   if (!guard.ok) return ZKB_EBUSY;
   if (!d || !out) return set_error(ctx, ZKB_EINVAL, "null argument");
   const uint64_t n = 1ull << d->log_n, m = d->n_vars, n_inst = uint64_t(d->n_public) + 1;
+  if (d->h_basis > 1) return set_error(ctx, ZKB_EINVAL, "unknown h_basis");
+  const bool snark = d->h_basis == 1;       // A already carries the input rows, C may be absent
   if (d->log_n < 1 || d->log_n > 26 || m < n_inst || m >= (1ull << 31) ||
-      d->n_constraints + n_inst > n || n_inst > 64)
+      d->n_constraints + (snark ? 0 : n_inst) > n || n_inst > 64)
     return set_error(ctx, ZKB_EINVAL, "inconsistent circuit dimensions (domain must hold constraints + instance)");
-  for (int k = 0; k < 3; k++)
+  const int n_mat = (snark && !d->row_ptr[2]) ? 2 : 3;
+  for (int k = 0; k < n_mat; k++)
     if (!d->row_ptr[k] || (d->row_ptr[k][d->n_constraints] && (!d->col[k] || !d->coeff[k])))
       return set_error(ctx, ZKB_EINVAL, "null matrix");
   if (!d->a_query || !d->b_g1_query || !d->b_g2_query || !d->h_query || (m > n_inst && !d->l_query) ||
@@ -617,7 +637,8 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     pk->m = m;
     pk->ncons = d->n_constraints;
     pk->n_inst = uint32_t(n_inst);
-    const uint64_t qlen[5] = {m, m, m, m, n - 1};
+    pk->h_basis = d->h_basis;
+    const uint64_t qlen[5] = {m, m, m, m, snark ? n : n - 1};
     for (int q = 0; q < 5; q++) pk->qcount[q] = qlen[q];
     // matrices: validate, de-duplicate coefficients into a table
     HostR1CS cs;
@@ -626,6 +647,10 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     std::vector<HFr> coeff_m;
     std::map<std::array<uint64_t, 4>, uint32_t> seen;
     for (int k = 0; k < 3; k++) {
+      if (k >= n_mat) {                      // no C matrix: an empty one keeps the uploads uniform
+        cs.row_ptr[k].assign(cs.ncons + 1, 0);
+        continue;
+      }
       const uint32_t nnz = d->row_ptr[k][cs.ncons];
       cs.row_ptr[k].assign(d->row_ptr[k], d->row_ptr[k] + cs.ncons + 1);
       cs.col[k].assign(d->col[k], d->col[k] + nnz);
@@ -653,7 +678,7 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     if ((rc = bases_from_bytes(ctx, d->b_g2_query, m, 0, 1, &pk->b_g2_query))) throw rc;
     // l_query arrives without the instance entries (ark-groth16); stored padded, see zkb_pk_query
     if ((rc = bases_from_bytes(ctx, d->l_query, m - n_inst, n_inst, 0, &pk->l_query))) throw rc;
-    if ((rc = bases_from_bytes(ctx, d->h_query, n - 1, 0, 0, &pk->h_query))) throw rc;
+    if ((rc = bases_from_bytes(ctx, d->h_query, snark ? n : n - 1, 0, 0, &pk->h_query))) throw rc;
     if (ctx->pk_precompute) {
       zkb_bases* qs[5] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query};
       for (zkb_bases* q : qs)
@@ -676,6 +701,16 @@ int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, zkb_pk** out) {
     zkb_bases_free(b2);
     if (e != cudaSuccess) throw cuda_fail(ctx, e, "fixed points");
     if ((rc = pk_upload_circuit(ctx, pk, cs, coeff_m))) throw rc;
+    if (snark) {
+      // coset shift of the witness map: the odd points of the size-2n domain are w_2n * <w_n>
+      uint32_t w2n[8], onew[8];
+      host_fr_root(d->log_n + 1, 0, w2n);
+      hfr_words(HFr::one(), onew);
+      cudaError_t e2 = cudaMalloc(&pk->d_shift, n * 32);
+      if (e2 != cudaSuccess) throw cuda_fail(ctx, e2, "coset shift table");
+      fr_powers_launch(pk->d_shift, w2n, onew, n, 1, ctx->stream);
+      if ((e2 = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) throw cuda_fail(ctx, e2, "coset shift table");
+    }
   } catch (int code) {
     zkb_pk_free(pk);
     return code;
@@ -709,19 +744,31 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     fr_to_mont_copy_kernel<<<bl_m, 256, 0, st>>>((const Fr*)pk->d_z, (Fr*)pk->d_zm, m);
     count_launches(5);   // + three SpMV launches and the pointwise kernel below
     void* outs[3] = {pk->d_a, pk->d_b, pk->d_c};
-    for (int k = 0; k < 3; k++)
+    const bool snark = pk->h_basis == 1;
+    for (int k = 0; k < (snark ? 2 : 3); k++)
       r1cs_spmv_kernel<<<bl_n, 256, 0, st>>>(pk->d_row_ptr[k], pk->d_col[k], pk->d_cidx[k],
                                              (const Fr*)pk->d_coeff_table, (const Fr*)pk->d_zm,
-                                             (Fr*)outs[k], pk->ncons, n, k == 0, pk->n_inst, pk->log_n, 0, 0, 0);
+                                             (Fr*)outs[k], pk->ncons, n, k == 0 && !snark, pk->n_inst, pk->log_n, 0, 0, 0);
+    if (snark) qap_product_kernel<<<bl_n, 256, 0, st>>>((const Fr*)pk->d_a, (const Fr*)pk->d_b, (Fr*)pk->d_c, n);
     mark(E_SPMV);
-    CosetTables* ct;
-    if ((rc = coset_tables(ctx, pk->log_n, &ct))) break;
-    for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 1, nullptr, nullptr, 0, 1, 1);
-    for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 0, ct->fwd.p, nullptr, 0, 1, 1);
-    if (rc) break;
-    qap_pointwise_kernel<<<bl_n, 256, 0, st>>>((Fr*)pk->d_a, (const Fr*)pk->d_b, (const Fr*)pk->d_c, n);
-    // coset iNTT with g^{-i} / Z(g) folded into the output table; result canonical = h
-    if ((rc = ntt_run(ctx, pk->d_a, pk->d_a, pk->log_n, 1, nullptr, ct->inv_z.p, 0, 1, 0))) break;
+    if (snark) {
+      // snarkjs witness map: a, b, c to coefficients, out to the odd points of the size-2n domain
+      // (coset shift w_2n), a*b - c there — no division by Z, no way back: six transforms
+      for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 1, nullptr, nullptr, 0, 1, 1);
+      for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 0, pk->d_shift, nullptr, 0, 1, 1);
+      if (rc) break;
+      qap_pointwise_canonical_kernel<<<bl_n, 256, 0, st>>>((Fr*)pk->d_a, (const Fr*)pk->d_b, (const Fr*)pk->d_c, n);
+      count_launches(1);
+    } else {
+      CosetTables* ct;
+      if ((rc = coset_tables(ctx, pk->log_n, &ct))) break;
+      for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 1, nullptr, nullptr, 0, 1, 1);
+      for (int k = 0; k < 3 && !rc; k++) rc = ntt_run(ctx, outs[k], outs[k], pk->log_n, 0, ct->fwd.p, nullptr, 0, 1, 1);
+      if (rc) break;
+      qap_pointwise_kernel<<<bl_n, 256, 0, st>>>((Fr*)pk->d_a, (const Fr*)pk->d_b, (const Fr*)pk->d_c, n);
+      // coset iNTT with g^{-i} / Z(g) folded into the output table; result canonical = h
+      if ((rc = ntt_run(ctx, pk->d_a, pk->d_a, pk->log_n, 1, nullptr, ct->inv_z.p, 0, 1, 0))) break;
+    }
     mark(E_NTT);
     {
       // A, B1, L (G1) and B2 (G2) all take the witness as scalars: one digits + sort, four walks; the
@@ -735,7 +782,7 @@ static int prove_msm_phase(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
     mark(E_H);
     if (results_out_opt)
       cudaMemcpyAsync(results_out_opt, pk->d_results, ZKB_INTERMEDIATE_BYTES, cudaMemcpyDeviceToHost, st);
-    if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);
+    if (h_out_opt) cudaMemcpyAsync(h_out_opt, pk->d_a, (n - 1) * 32, cudaMemcpyDeviceToHost, st);   // snarkjs keys: the first n - 1 H scalars
     cudaMemcpyAsync(&bad_flag, ctx->msm.flag.p, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -909,6 +956,7 @@ int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* wit
 int zkb_groth16_witness_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witness, void* d_abc_out[3]) {
   ZKB_PK_ENTER(ctx, pk);
   if (!witness || !d_abc_out) return set_error(ctx, ZKB_EINVAL, "null argument");
+  if (pk->h_basis) return set_error(ctx, ZKB_EINVAL, "snarkjs-basis key: zkb_groth16_prove / _prove_partial only");
   int rc = prove_witness_phase(ctx, pk, witness);
   d_abc_out[0] = pk->d_a;
   d_abc_out[1] = pk->d_b;
@@ -923,6 +971,7 @@ int zkb_groth16_witness_layout_dev(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t
     return set_error(ctx, ZKB_EINVAL, "null argument");
   if (low_bits == 0 || low_bits >= pk->log_n || world == 0 || rank >= world || ((1u << low_bits) % world))
     return set_error(ctx, ZKB_EINVAL, "bad layout argument");
+  if (pk->h_basis) return set_error(ctx, ZKB_EINVAL, "snarkjs-basis key: zkb_groth16_prove / _prove_partial only");
   return prove_witness_phase(ctx, pk, witness, low_bits, world, rank, d_abc_local);
 }
 
@@ -959,6 +1008,7 @@ int zkb_groth16_prove_dist(zkb_ctx* ctx, const zkb_pk* pk, const uint8_t* witnes
   const uint32_t L = pk->log_n, d0 = dist_low_bits(L), d1 = L - d0, G = uint32_t(cm->world), g = uint32_t(cm->rank);
   if (pk->world != G || pk->rank != g || pk->h_low_bits != d1)
     return set_error(ctx, ZKB_EINVAL, "key was not built for this communicator (use zkb_pk_synthetic_dist)");
+  if (pk->h_basis) return set_error(ctx, ZKB_EINVAL, "snarkjs-basis key: single-GPU prove only");
   const uint64_t n = pk->n, m = pk->m, n_loc = n / G;
   cudaStream_t st = ctx->stream;
   enum { E_START, E_WIT, E_SPMV, E_NTT, E_A, E_B1, E_L, E_B2, E_MSMH, E_END, E_COUNT };

@@ -25,7 +25,7 @@ EXPORTS = [
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
     "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_proof_check",
-    "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read",
+    "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read", "zkb_zkey_inspect", "zkb_zkey_read",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings", "zkb_host_alloc", "zkb_host_free", "zkb_pk_n_vars", "zkb_pk_log_n",
     "zkb_comm_unique_id", "zkb_comm_init", "zkb_comm_init_local", "zkb_comm_rank", "zkb_comm_world",
@@ -48,7 +48,8 @@ class PkDesc(C.Structure):
                 ("row_ptr", C.c_void_p * 3), ("col", C.c_void_p * 3), ("coeff", C.c_void_p * 3),
                 ("a_query", C.c_void_p), ("b_g1_query", C.c_void_p), ("b_g2_query", C.c_void_p),
                 ("l_query", C.c_void_p), ("h_query", C.c_void_p), ("alpha_g1", C.c_void_p), ("beta_g1", C.c_void_p),
-                ("delta_g1", C.c_void_p), ("beta_g2", C.c_void_p), ("delta_g2", C.c_void_p)]
+                ("delta_g1", C.c_void_p), ("beta_g2", C.c_void_p), ("delta_g2", C.c_void_p),
+                ("h_basis", C.c_uint32)]
 
 
 class ProveTimings(C.Structure):
@@ -66,6 +67,17 @@ class R1csInfo(C.Structure):
     _fields_ = [("n_wires", C.c_uint32), ("n_pub_out", C.c_uint32), ("n_pub_in", C.c_uint32),
                 ("n_prv_in", C.c_uint32), ("n_constraints", C.c_uint32), ("n_labels", C.c_uint64),
                 ("nnz", C.c_uint64 * 3)]
+
+
+class ZkeyInfo(C.Structure):
+    _fields_ = [("n_vars", C.c_uint32), ("n_public", C.c_uint32), ("log_n", C.c_uint32), ("n_rows", C.c_uint32),
+                ("nnz", C.c_uint64 * 2)]
+
+
+class ZkeyData(C.Structure):
+    _fields_ = [("row_ptr", C.c_void_p * 2), ("col", C.c_void_p * 2), ("coeff", C.c_void_p * 2)] + [
+        (n, C.c_void_p) for n in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "gamma_g2", "delta_g2", "ic",
+                                  "a_query", "b_g1_query", "b_g2_query", "c_query", "h_query")]
 
 
 def load_library() -> C.CDLL:
@@ -156,6 +168,8 @@ def load_library() -> C.CDLL:
     lib.zkb_r1cs_read.argtypes = [u8p, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.zkb_wtns_inspect.argtypes = [u8p, u64, C.POINTER(u32)]
     lib.zkb_wtns_read.argtypes = [u8p, u64, vp]
+    lib.zkb_zkey_inspect.argtypes = [u8p, u64, C.POINTER(ZkeyInfo)]
+    lib.zkb_zkey_read.argtypes = [u8p, u64, C.POINTER(ZkeyData)]
     lib.zkb_field_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_curve_batch_op.argtypes = [vp, i32, i32, u8p, u8p, vp, u64]
     lib.zkb_bench_int_pipe.argtypes = [vp, i32, C.POINTER(C.c_double)]
@@ -381,18 +395,23 @@ class Context:
         self._check(self.lib.zkb_pk_synthetic_shard_ex(self.h, log_n, seed, rank, world, h_low_bits, C.byref(h), vk))
         return ProvingKey(self, h, vk.raw, log_n)
 
-    def pk_load(self, log_n: int, n_vars: int, n_public: int, matrices, queries: dict, fixed: dict, vk: bytes = b"") -> ProvingKey:
+    def pk_load(self, log_n: int, n_vars: int, n_public: int, matrices, queries: dict, fixed: dict, vk: bytes = b"",
+                h_basis: int = 0) -> ProvingKey:
         """matrices: three (row_ptr list[int], col list[int], coeff bytes) for A, B, C;
         queries: a_query, b_g1_query, b_g2_query, l_query, h_query (canonical affine bytes);
-        fixed: alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2."""
+        fixed: alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2.
+        h_basis = 1 (a snarkjs .zkey, see circom_io.read_zkey): matrices may hold A and B only, A
+        includes the input rows, h_query holds 2^log_n points."""
         import array
         d = PkDesc()
-        d.log_n, d.n_public, d.n_vars = log_n, n_public, n_vars
+        d.log_n, d.n_public, d.n_vars, d.h_basis = log_n, n_public, n_vars, h_basis
+        if h_basis not in (0, 1) or len(matrices) not in ((3,) if h_basis == 0 else (2, 3)):
+            raise ValueError("h_basis 0 takes A, B, C; h_basis 1 takes A, B and optionally C")
         d.n_constraints = len(matrices[0][0]) - 1
         # the C ABI takes bare pointers: every array length is checked here against the dimensions
         n = 1 << log_n
         want = {"a_query": 64 * n_vars, "b_g1_query": 64 * n_vars, "b_g2_query": 128 * n_vars,
-                "l_query": 64 * max(n_vars - n_public - 1, 0), "h_query": 64 * (n - 1)}
+                "l_query": 64 * max(n_vars - n_public - 1, 0), "h_query": 64 * (n if h_basis else n - 1)}
         for name, size in want.items():
             if len(queries[name]) != size:
                 raise ValueError("%s holds %d bytes, expected %d" % (name, len(queries[name]), size))

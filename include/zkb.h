@@ -196,7 +196,8 @@ int zkb_pk_synthetic_shard(zkb_ctx* ctx, uint32_t log_n, uint64_t seed, uint32_t
  * Matrices are CSR over the variables z = (1, public..., private...): row_ptr has n_constraints + 1
  * entries, coeff holds one canonical 32-byte Fr per non-zero.  Queries are the fields of
  * ark-groth16's ProvingKey as canonical affine bytes (all-zero = infinity): a_query, b_g1_query,
- * b_g2_query have n_vars points, l_query n_vars - n_public - 1, h_query 2^log_n - 1.  The domain
+ * b_g2_query have n_vars points, l_query n_vars - n_public - 1, h_query 2^log_n - 1 (h_basis 0;
+ * see h_basis for snarkjs keys).  The domain
  * must satisfy n_constraints + n_public + 1 <= 2^log_n (ark-groth16 appends one input-consistency
  * row per instance variable).  Everything is copied; the caller's buffers can be freed after. */
 typedef struct zkb_pk_desc {
@@ -210,6 +211,13 @@ typedef struct zkb_pk_desc {
   const uint8_t *a_query, *b_g1_query, *b_g2_query, *l_query, *h_query;
   const uint8_t *alpha_g1, *beta_g1, *delta_g1;   /* 64 B each */
   const uint8_t *beta_g2, *delta_g2;              /* 128 B each */
+  /* 0: ark-groth16 (above).  1: snarkjs (.zkey): h_query holds 2^log_n points L_{2i+1}(tau) / delta
+   * (Lagrange basis of the size-2^(log_n+1) domain at its odd points) and the prover evaluates
+   * a * b - c on those points instead of dividing by the vanishing polynomial; matrix A already
+   * contains the input rows (n_constraints counts them, n_constraints <= 2^log_n) and matrix C may be
+   * null (row_ptr[2] == NULL: c = a * b on the domain).  Same proof bytes as h_basis 0 for the same
+   * circuit, setup, witness and (r, s).  Single-GPU prove only. */
+  uint32_t h_basis;
 } zkb_pk_desc;
 int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* desc, zkb_pk** out);
 /* as above, with h_query held in the output layout of the four-step NTT: local [low_loc][high]
@@ -326,6 +334,33 @@ int zkb_r1cs_read(const uint8_t* file, uint64_t len, uint32_t* const row_ptr[3],
                   uint8_t* const coeff[3]);
 int zkb_wtns_inspect(const uint8_t* file, uint64_t len, uint32_t* n_witness_out);
 int zkb_wtns_read(const uint8_t* file, uint64_t len, uint8_t* witness_out);
+/* snarkjs / rapidsnark Groth16 proving keys (.zkey, BN254).  The container stores points as affine
+ * coordinates in Montgomery form and matrix coefficients times 2^512 mod r; the reader hands back
+ * canonical little-endian values (all-zero point = infinity), ready for zkb_pk_desc with
+ * h_basis = 1.  Only A and B are stored (a prover takes c = a * b on the domain), A includes the
+ * n_public + 1 input rows, and entries may come in any order: the reader builds CSR with n_rows =
+ * highest row index + 1.  Buffers (caller-allocated from zkb_zkey_info): row_ptr[k] n_rows + 1,
+ * col[k] nnz[k], coeff[k] 32 * nnz[k]; alpha_g1 / beta_g1 / delta_g1 64; beta_g2 / gamma_g2 /
+ * delta_g2 128; ic 64 * (n_public + 1); a_query, b_g1_query 64 * n_vars; b_g2_query 128 * n_vars;
+ * c_query 64 * (n_vars - n_public - 1); h_query 64 * 2^log_n.  Null output pointers are skipped.
+ * ZKB_EINVAL for a bad magic / version / protocol / prime / truncated or mis-sized section / an
+ * index out of range / a value that is not reduced.  Points are NOT checked for curve membership
+ * here; zkb_pk_load does that on the device.  The layout is restated, with a writer, in the test
+ * tree; it is not pinned against a file written by snarkjs itself (none exists in this build
+ * environment). */
+typedef struct zkb_zkey_info {
+  uint32_t n_vars, n_public, log_n, n_rows;
+  uint64_t nnz[2];   /* non-zeros of A, B */
+} zkb_zkey_info;
+typedef struct zkb_zkey_data {
+  uint32_t* row_ptr[2];
+  uint32_t* col[2];
+  uint8_t* coeff[2];
+  uint8_t *alpha_g1, *beta_g1, *delta_g1, *beta_g2, *gamma_g2, *delta_g2, *ic;
+  uint8_t *a_query, *b_g1_query, *b_g2_query, *c_query, *h_query;
+} zkb_zkey_data;
+int zkb_zkey_inspect(const uint8_t* file, uint64_t len, zkb_zkey_info* out);
+int zkb_zkey_read(const uint8_t* file, uint64_t len, const zkb_zkey_data* out);
 
 /* ---- test / measurement hooks ------------------------------------------------------------------ */
 /* element-wise field ops on host arrays of canonical elements, executed by the device field

@@ -56,6 +56,8 @@ pub struct zkb_pk_desc {
     pub l_query: *const u8, pub h_query: *const u8,
     pub alpha_g1: *const u8, pub beta_g1: *const u8, pub delta_g1: *const u8,
     pub beta_g2: *const u8, pub delta_g2: *const u8,
+    /// 0 = ark-groth16 h_query, 1 = snarkjs .zkey H section (see include/zkb.h)
+    pub h_basis: u32,
 }
 
 /// sizes of an iden3 .r1cs file (see include/zkb.h `zkb_r1cs_info`)
@@ -65,6 +67,26 @@ pub struct zkb_r1cs_info {
     pub n_wires: u32, pub n_pub_out: u32, pub n_pub_in: u32, pub n_prv_in: u32, pub n_constraints: u32,
     pub n_labels: u64,
     pub nnz: [u64; 3],
+}
+
+/// sizes of a snarkjs Groth16 .zkey file (see include/zkb.h `zkb_zkey_info`)
+#[repr(C)]
+#[derive(Debug, Default, Clone, Copy)]
+pub struct zkb_zkey_info {
+    pub n_vars: u32, pub n_public: u32, pub log_n: u32, pub n_rows: u32,
+    pub nnz: [u64; 2],
+}
+
+/// caller-allocated outputs of `zkb_zkey_read` (null pointers are skipped)
+#[repr(C)]
+pub struct zkb_zkey_data {
+    pub row_ptr: [*mut u32; 2],
+    pub col: [*mut u32; 2],
+    pub coeff: [*mut u8; 2],
+    pub alpha_g1: *mut u8, pub beta_g1: *mut u8, pub delta_g1: *mut u8,
+    pub beta_g2: *mut u8, pub gamma_g2: *mut u8, pub delta_g2: *mut u8, pub ic: *mut u8,
+    pub a_query: *mut u8, pub b_g1_query: *mut u8, pub b_g2_query: *mut u8,
+    pub c_query: *mut u8, pub h_query: *mut u8,
 }
 
 #[link(name = "zkb")]
@@ -143,6 +165,8 @@ extern "C" {
     pub fn zkb_r1cs_read(file: *const u8, len: u64, row_ptr: *mut *mut u32, col: *mut *mut u32, coeff: *mut *mut u8) -> c_int;
     pub fn zkb_wtns_inspect(file: *const u8, len: u64, n_witness_out: *mut u32) -> c_int;
     pub fn zkb_wtns_read(file: *const u8, len: u64, witness_out: *mut u8) -> c_int;
+    pub fn zkb_zkey_inspect(file: *const u8, len: u64, out_: *mut zkb_zkey_info) -> c_int;
+    pub fn zkb_zkey_read(file: *const u8, len: u64, out_: *const zkb_zkey_data) -> c_int;
     pub fn zkb_field_batch_op(ctx: *mut zkb_ctx, field: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_curve_batch_op(ctx: *mut zkb_ctx, group: c_int, op: c_int, a: *const u8, b: *const u8, out_: *mut u8, n: u64) -> c_int;
     pub fn zkb_bench_int_pipe(ctx: *mut zkb_ctx, iters: c_int, results: *mut f64) -> c_int;

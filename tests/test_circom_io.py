@@ -116,3 +116,107 @@ def test_parsers_survive_mutated_files(cio, zkb):
         except zkb.ZkbError:
             rejected += 1
     assert rejected > 1000
+
+
+# ---------------------------------------------------------------------------- .zkey (snarkjs Groth16 key)
+@pytest.fixture(scope="module")
+def zkey_case():
+    """a tiny circuit, its Oracle A setup, and the .zkey bytes oracle_zkey writes for it"""
+    import oracle_zkey as zkm
+    cs, z = small_circuit(5)
+    rng = o.Xoshiro256ss(0x2E7)
+    tau, alpha, beta, gamma, delta, r, s = [rng.fr() or 1 for _ in range(7)]
+    pk, vk = o.groth16_setup(cs, tau, alpha, beta, gamma, delta)
+    data = zkm.zkey_bytes(cs, pk, vk, zkm.h_points_snarkjs(tau, delta, pk["n"]))
+    return cs, z, pk, vk, r, s, data
+
+
+def test_zkey_snarkjs_witness_map_gives_the_ark_proof(zkey_case):
+    """the oracle pins the maths the GPU path relies on: the H section L_{2i+1}(tau)/delta with
+    (ab - c) on the odd points of the size-2n domain yields the SAME proof bytes as ark-groth16's
+    tau^i Z(tau)/delta with h = (ab - c)/Z, and the proof verifies under the key's own vk"""
+    import oracle_zkey as zkm
+    cs, z, pk, vk, r, s, data = zkey_case
+    zk = zkm.zkey_parse(data)
+    p_ark, i_ark = o.groth16_prove(pk, cs, z, r, s)
+    p_zk, i_zk = zkm.groth16_prove_zkey(zk, z, r, s)
+    assert p_zk == p_ark and i_zk["msm_h"] == i_ark["msm_h"]
+    assert i_zk["a_evals"] == i_ark["a_evals"] and i_zk["b_evals"] == i_ark["b_evals"] and i_zk["c_evals"] == i_ark["c_evals"]
+    assert o.groth16_verify(zkm.vk_of(zk), p_zk, [z[1]])
+    assert not o.groth16_verify(zkm.vk_of(zk), p_zk, [(z[1] + 1) % o.R])
+
+
+def test_zkey_reader_matches_the_oracle_parser(cio, zkey_case):
+    import oracle_zkey as zkm
+    cs, z, pk, vk, r, s, data = zkey_case
+    zk, ref = cio.read_zkey(data), zkm.zkey_parse(data)
+    n_cons = len(cs["A"])
+    assert (zk.n_vars, zk.n_public, 1 << zk.log_n, zk.n_rows) == (cs["m"], 1, pk["n"], n_cons + 2)
+    g1s = lambda pts: b"".join(o.g1_to_bytes(P) for P in pts)
+    assert zk.queries["a_query"] == g1s(ref["a_query"]) == g1s(pk["a_query"])
+    assert zk.queries["b_g1_query"] == g1s(ref["b_g1_query"])
+    assert zk.queries["b_g2_query"] == b"".join(o.g2_to_bytes(P) for P in ref["b_g2_query"])
+    assert zk.queries["l_query"] == g1s(ref["c_query"]) == g1s(pk["l_query"])
+    assert zk.queries["h_query"] == g1s(ref["h_query"]) and len(zk.queries["h_query"]) == 64 * pk["n"]
+    for name in ("alpha_g1", "beta_g1", "delta_g1"):
+        assert zk.fixed[name] == o.g1_to_bytes(ref[name])
+    for name in ("beta_g2", "gamma_g2", "delta_g2"):
+        assert zk.fixed[name] == o.g2_to_bytes(ref[name])
+    assert zk.ic == g1s(vk["gamma_abc_g1"])
+    assert zk.vk_bytes() == (o.g1_to_bytes(vk["alpha_g1"]) + o.g2_to_bytes(vk["beta_g2"]) + o.g2_to_bytes(vk["gamma_g2"])
+                             + o.g2_to_bytes(vk["delta_g2"]) + g1s(vk["gamma_abc_g1"]))
+    # CSR of A (with the input rows) and B == the coefficient list, whatever order the file lists it in
+    want = [{}, {}]
+    for mat, row, sig, v in ref["coeffs"]:
+        want[mat].setdefault(row, []).append((sig, v))
+    for k in range(2):
+        rp, col, co = zk.matrices[k]
+        got = {}
+        for row in range(zk.n_rows):
+            for t in range(rp[row], rp[row + 1]):
+                got.setdefault(row, []).append((col[t], int.from_bytes(co[32 * t:32 * t + 32], "little")))
+        assert got == want[k]
+    assert want[0][n_cons] == [(0, 1)] and want[0][n_cons + 1] == [(1, 1)]
+
+
+def test_zkey_entries_in_any_order_and_malformed_files(cio, zkb, zkey_case):
+    import oracle_zkey as zkm
+    cs, z, pk, vk, r, s, data = zkey_case
+    zk = cio.read_zkey(data)
+    ref = zkm.zkey_parse(data)
+    # the same key with the coefficient entries reversed reads to the same matrices up to the order inside a row
+    g1s = lambda pts: b"".join(o.g1_to_bytes(P) for P in pts)
+    fixed = dict(zk.fixed)
+    rev = zkm.zkey_bytes_raw(zk.n_vars, zk.n_public, 1 << zk.log_n, ref["coeffs"][::-1], fixed, zk.ic,
+                             zk.queries["a_query"], zk.queries["b_g1_query"], zk.queries["b_g2_query"],
+                             zk.queries["l_query"], zk.queries["h_query"])
+    zr = cio.read_zkey(rev)
+    assert zr.queries == zk.queries and zr.fixed == zk.fixed and zr.ic == zk.ic
+    for k in range(2):
+        assert zr.matrices[k][0] == zk.matrices[k][0]
+        rows = lambda mz: [sorted((mz[1][t], mz[2][32 * t:32 * t + 32]) for t in range(mz[0][j], mz[0][j + 1]))
+                           for j in range(zk.n_rows)]
+        assert rows(zr.matrices[k]) == rows(zk.matrices[k])
+
+    def bad(mutated):
+        with pytest.raises(zkb.ZkbError):
+            cio.read_zkey(bytes(mutated))
+
+    bad(b"zkez" + data[4:])                                      # magic
+    bad(data[:4] + struct.pack("<I", 2) + data[8:])              # version
+    bad(data[:-1])                                               # truncated last section
+    bad(data[:len(data) // 2])
+    i = data.index(struct.pack("<IQ", 1, 4)) + 12
+    bad(data[:i] + struct.pack("<I", 2) + data[i + 4:])          # protocol 2 = plonk
+    h = data.index(o.Q.to_bytes(32, "little"))
+    bad(data[:h] + o.R.to_bytes(32, "little") + data[h + 32:])   # another base field
+    # a coordinate that is not reduced (first point of section 5 := q)
+    s5 = data.index(struct.pack("<IQ", 5, 64 * zk.n_vars)) + 12
+    bad(data[:s5] + o.Q.to_bytes(32, "little") + data[s5 + 32:])
+    # coefficient entry with a signal / row / matrix out of range, and a value >= r
+    s4 = data.index(struct.pack("<IQ", 4, 4 + 44 * len(ref["coeffs"]))) + 12
+    bad(data[:s4 + 4] + struct.pack("<I", 2) + data[s4 + 8:])
+    bad(data[:s4 + 8] + struct.pack("<I", 1 << zk.log_n) + data[s4 + 12:])
+    bad(data[:s4 + 12] + struct.pack("<I", zk.n_vars) + data[s4 + 16:])
+    bad(data[:s4 + 16] + o.R.to_bytes(32, "little") + data[s4 + 48:])
+    bad(data[:s4] + struct.pack("<I", len(ref["coeffs"]) + 1) + data[s4 + 4:])   # count disagrees with the section size
