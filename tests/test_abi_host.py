@@ -221,14 +221,76 @@ def test_rust_sys_crate_is_in_sync_with_the_header():
     assert 'cargo:rustc-link-lib=dylib=zkb' in open(os.path.join(ROOT, "rust", "zkb-sys", "build.rs")).read()
 
 
-def _build_example(tmp_path):
+def _build_example(tmp_path, name="prove_cli"):
     import subprocess
-    exe = str(tmp_path / "prove_cli")
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "eigen-zeth_b200")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "examples", "prove_cli.cpp"), "-L" + libdir, "-lzkb",
+                    os.path.join(ROOT, "examples", name + ".cpp"), "-L" + libdir, "-lzkb",
                     "-Wl,-rpath," + libdir, "-o", exe], check=True)
     return exe
+
+
+def _zkey_case(tmp_path):
+    """a small circuit as the files a circom / snarkjs flow leaves behind: circuit.zkey + witness.wtns"""
+    import oracle_a as o
+    import oracle_zkey as zkm
+    from eigen_zeth_b200 import circom_io as cio
+    from helpers import small_circuit
+    cs, z = small_circuit(6)
+    rng = o.Xoshiro256ss(0x2E71)
+    tau, alpha, beta, gamma, delta = [rng.fr() or 1 for _ in range(5)]
+    pk, vk = o.groth16_setup(cs, tau, alpha, beta, gamma, delta)
+    zpath, wpath = str(tmp_path / "circuit.zkey"), str(tmp_path / "witness.wtns")
+    open(zpath, "wb").write(zkm.zkey_bytes(cs, pk, vk, zkm.h_points_snarkjs(tau, delta, pk["n"])))
+    open(wpath, "wb").write(cio.write_wtns(z))
+    return cs, z, vk, zpath, wpath
+
+
+def test_zkey_prover_example_parses_before_touching_the_gpu(tmp_path):
+    """examples/zkey_prover.cpp (the rapidsnark-style command line over the C ABI): malformed inputs
+    exit 1 whatever the machine, a good pair exits 2 on a machine without a GPU"""
+    import subprocess
+    import torch
+    from eigen_zeth_b200 import circom_io as cio
+    exe = _build_example(tmp_path, "zkey_prover")
+    cs, z, vk, zpath, wpath = _zkey_case(tmp_path)
+    out = [str(tmp_path / "proof.json"), str(tmp_path / "public.json")]
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, timeout=120)
+    r = run(zpath)
+    assert r.returncode == 1 and "usage" in r.stderr
+    junk = str(tmp_path / "junk.zkey")
+    open(junk, "wb").write(open(zpath, "rb").read()[:300])
+    r = run(junk, wpath, *out)
+    assert r.returncode == 1 and "not a BN254 Groth16 .zkey" in r.stderr
+    short = str(tmp_path / "short.wtns")
+    open(short, "wb").write(cio.write_wtns(z[:-1]))
+    r = run(zpath, short, *out)
+    assert r.returncode == 1 and "the key has %d variables" % cs["m"] in r.stderr
+    assert not os.path.exists(out[0])
+    if not torch.cuda.is_available():
+        r = run(zpath, wpath, *out)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr and not os.path.exists(out[0])
+
+
+@pytest.mark.gpu
+def test_zkey_prover_example_writes_a_proof_the_oracle_verifies(tmp_path):
+    import json
+    import subprocess
+    import oracle_a as o
+    exe = _build_example(tmp_path, "zkey_prover")
+    cs, z, vk, zpath, wpath = _zkey_case(tmp_path)
+    out = [str(tmp_path / "proof.json"), str(tmp_path / "public.json")]
+    r = subprocess.run([exe, zpath, wpath, *out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pairing check passed" in r.stderr, r.stderr
+    proof = o.parse_proof(open(out[0]).read())
+    public = [int(x) for x in json.load(open(out[1]))]
+    assert public == [z[1]]
+    assert o.groth16_verify(vk, proof, public)
+    # fresh blinding every run: another proof of the same statement, still valid
+    r = subprocess.run([exe, zpath, wpath, *out], capture_output=True, text=True, timeout=300)
+    proof2 = o.parse_proof(open(out[0]).read())
+    assert r.returncode == 0 and proof2 != proof and o.groth16_verify(vk, proof2, public)
 
 
 def test_cpp_example_builds_against_the_c_abi_and_fails_loudly_without_gpu(tmp_path):
