@@ -86,10 +86,14 @@ class Zkey:
     ic: bytes               # 64 * (n_public + 1)
     queries: dict           # a_query, b_g1_query, b_g2_query, l_query (the key's C section), h_query
 
+    def vk_fixed(self) -> bytes:
+        """alpha_g1 | beta_g2 | gamma_g2 | delta_g2: the first argument of zkb_groth16_verify_ex (ic is the second)"""
+        f = self.fixed
+        return f["alpha_g1"] + f["beta_g2"] + f["gamma_g2"] + f["delta_g2"]
+
     def vk_bytes(self) -> bytes:
         """the verifying key in the library's layout (one public input: ZKB_VK_BYTES = 576)"""
-        f = self.fixed
-        return f["alpha_g1"] + f["beta_g2"] + f["gamma_g2"] + f["delta_g2"] + self.ic
+        return self.vk_fixed() + self.ic
 
 
 def read_zkey(data: bytes) -> Zkey:

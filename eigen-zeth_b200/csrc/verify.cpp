@@ -459,6 +459,24 @@ bool read_g2(const uint8_t* b, G2* p) {
          read_fq(b + 96, &p->y.b) && g2_on_curve(*p) && g2_in_subgroup(*p);
 }
 
+// e(A,B) e(-alpha,beta) e(-acc,gamma) e(-C,delta) == 1: one shared Miller loop, one final exponentiation
+int pairing_check(const G1& A, const G2& B, const G1& C, const G1& alpha, const G2& beta, const G2& gamma,
+                  const G2& delta, const G1& acc) {
+  static const Frob fr;
+  auto negp = [](G1 p) { p.y = p.y.neg(); return p; };
+  const G1 Ps[4] = {A, negp(alpha), negp(acc), negp(C)};
+  const G2 Qs[4] = {B, beta, gamma, delta};
+  G1 P[4];
+  G2 Q[4];
+  int n = 0;
+  for (int k = 0; k < 4; k++)
+    if (!Ps[k].inf && !Qs[k].inf) {
+      P[n] = Ps[k];
+      Q[n++] = Qs[k];
+    }
+  return final_exp(multi_miller(P, Q, n, fr)) == F12::one() ? ZKB_OK : ZKB_EVERIFY;
+}
+
 }  // namespace
 
 extern "C" int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],
@@ -490,21 +508,28 @@ extern "C" int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t 
   uint64_t x[4];
   std::memcpy(x, public_input, 32);
   if (!HFr::lt_mod(x)) return ZKB_EINVAL;   // NewStateRootNotInsidePrime on-chain
-  G1 acc = g1_add(ic0, g1_mul(ic1, x));
-  static const Frob fr;
-  auto negp = [](G1 p) { p.y = p.y.neg(); return p; };
-  // e(A,B) e(-alpha,beta) e(-acc,gamma) e(-C,delta) == 1: one shared Miller loop, one final exponentiation
-  const G1 Ps[4] = {A, negp(alpha), negp(acc), negp(C)};
-  const G2 Qs[4] = {B, beta, gamma, delta};
-  G1 P[4];
-  G2 Q[4];
-  int n = 0;
-  for (int k = 0; k < 4; k++)
-    if (!Ps[k].inf && !Qs[k].inf) {
-      P[n] = Ps[k];
-      Q[n++] = Qs[k];
-    }
-  return final_exp(multi_miller(P, Q, n, fr)) == F12::one() ? ZKB_OK : ZKB_EVERIFY;
+  return pairing_check(A, B, C, alpha, beta, gamma, delta, g1_add(ic0, g1_mul(ic1, x)));
+}
+
+// any number of public inputs (keys of circuits other than the final-proof one): the key is
+// validated on every call
+extern "C" int zkb_groth16_verify_ex(const uint8_t vk_fixed[448], const uint8_t* ic, uint32_t n_public,
+                                     const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t* public_inputs) {
+  if (!vk_fixed || !ic || !proof || (n_public && !public_inputs)) return ZKB_EINVAL;
+  G1 alpha, A, C, acc;
+  G2 beta, gamma, delta, B;
+  if (!read_g1(vk_fixed, &alpha) || !read_g2(vk_fixed + 64, &beta) || !read_g2(vk_fixed + 192, &gamma) ||
+      !read_g2(vk_fixed + 320, &delta) || !read_g1(ic, &acc))
+    return ZKB_EINVAL;
+  if (!read_g1(proof, &A) || !read_g2(proof + 64, &B) || !read_g1(proof + 192, &C)) return ZKB_EINVAL;
+  for (uint32_t i = 0; i < n_public; i++) {
+    G1 p;
+    uint64_t x[4];
+    std::memcpy(x, public_inputs + 32ull * i, 32);
+    if (!read_g1(ic + 64ull * (i + 1), &p) || !HFr::lt_mod(x)) return ZKB_EINVAL;
+    acc = g1_add(acc, g1_mul(p, x));
+  }
+  return pairing_check(A, B, C, alpha, beta, gamma, delta, acc);
 }
 
 // ---------------------------------------------------------------- proof assembly (K15) on the host

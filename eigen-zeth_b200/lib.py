@@ -24,7 +24,7 @@ EXPORTS = [
     "zkb_msm_g1", "zkb_msm_g2", "zkb_msm_g1_dev", "zkb_msm_g2_dev", "zkb_g1_sum", "zkb_g2_sum",
     "zkb_pk_synthetic", "zkb_pk_synthetic_shard", "zkb_pk_load", "zkb_pk_free", "zkb_pk_query",
     "zkb_groth16_prove_partial", "zkb_groth16_assemble", "zkb_pk_synthetic_shard_ex", "zkb_groth16_witness_dev",
-    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_proof_check",
+    "zkb_groth16_msm_dev", "zkb_fr_gather_layout_dev", "zkb_groth16_witness_layout_dev", "zkb_synthetic_witness", "zkb_groth16_prove", "zkb_groth16_verify", "zkb_groth16_verify_ex", "zkb_proof_check",
     "zkb_r1cs_inspect", "zkb_r1cs_read", "zkb_wtns_inspect", "zkb_wtns_read", "zkb_zkey_inspect", "zkb_zkey_read",
     "zkb_field_batch_op", "zkb_curve_batch_op", "zkb_bench_int_pipe", "zkb_g1_sum_dev", "zkb_g2_sum_dev",
     "zkb_ctx_launches", "zkb_msm_last_timings", "zkb_host_alloc", "zkb_host_free", "zkb_pk_n_vars", "zkb_pk_log_n",
@@ -146,6 +146,7 @@ def load_library() -> C.CDLL:
         lib.zkb_synthetic_witness.argtypes = [u32, u8p, u8p, vp]
         lib.zkb_groth16_prove.argtypes = [vp, vp, vp, u8p, u8p, vp, vp, vp, C.POINTER(ProveTimings)]
         lib.zkb_groth16_verify.argtypes = [u8p, u8p, u8p]
+        lib.zkb_groth16_verify_ex.argtypes = [u8p, u8p, u32, u8p, u8p]
         lib.zkb_proof_check.argtypes = [u8p, u8p, C.POINTER(u32)]
         lib.zkb_selftest_final_exp.argtypes = [u8p]
         lib.zkb_groth16_assemble_host.argtypes = [u8p, u8p, u8p, u8p, vp]
@@ -678,6 +679,19 @@ def groth16_verify(vk: bytes, proof: bytes, public_input: bytes) -> bool:
     """CPU pairing check; False for an invalid proof, raises for a malformed one."""
     lib = load_library()
     rc = lib.zkb_groth16_verify(vk, proof, public_input)
+    if rc == ZKB_OK:
+        return True
+    if rc == ZKB_EVERIFY:
+        return False
+    raise ZkbError(rc, "malformed verifying key / proof / input")
+
+
+def groth16_verify_ex(vk_fixed: bytes, ic: bytes, proof: bytes, public_inputs: bytes) -> bool:
+    """the pairing check for any number of public inputs: vk_fixed = alpha_g1 | beta_g2 | gamma_g2 |
+    delta_g2 (448 bytes), ic = n_public + 1 G1 points, public_inputs = n_public canonical Fr"""
+    if len(vk_fixed) != 448 or len(ic) % 64 or len(ic) < 64 or len(public_inputs) != 32 * (len(ic) // 64 - 1) or len(proof) != PROOF_BYTES:
+        raise ValueError("vk_fixed 448 bytes, ic 64 * (n_public + 1), inputs 32 * n_public, proof 256")
+    rc = load_library().zkb_groth16_verify_ex(vk_fixed, ic, len(ic) // 64 - 1, proof, public_inputs or None)
     if rc == ZKB_OK:
         return True
     if rc == ZKB_EVERIFY:

@@ -4,9 +4,8 @@
 //   zkey_prover <circuit.zkey> <witness.wtns> <proof.json> <public.json>
 //
 // Reads a snarkjs Groth16 proving key and a circom witness (both parsed by libzkb.so), loads the key
-// with h_basis = 1, proves on the GPU with fresh blinding scalars, checks the pairing equation when
-// the circuit has one public input (the shape of eigen-zeth's final proof: ZKB_VK_BYTES holds ic0,
-// ic1) and writes the two files in the layout eigen-zeth stores and parses (reference
+// with h_basis = 1, proves on the GPU with fresh blinding scalars, checks the pairing equation under
+// the key's own verifying key and writes the two files in the layout eigen-zeth stores and parses (reference
 // proof/proof.json:1-22, proof/public_input.json:1-3, src/settlement/ethereum/mod.rs:445-481).
 // Exit codes: 0 proof written, 1 bad input / prover error, 2 no GPU (there is no CPU fallback).
 // Both files are parsed BEFORE the GPU is touched, so a malformed key fails the same way anywhere.
@@ -166,19 +165,14 @@ int main(int argc, char** argv) {
     fprintf(stderr, "prove: %s\n", zkb_last_error(ctx));
     return 1;
   }
-  bool checked = false, ok = true;
-  if (zi.n_public == 1) {
-    uint8_t vk[ZKB_VK_BYTES];
-    std::memcpy(vk, zd.alpha_g1, 64);
-    std::memcpy(vk + 64, zd.beta_g2, 128);
-    std::memcpy(vk + 192, zd.gamma_g2, 128);
-    std::memcpy(vk + 320, zd.delta_g2, 128);
-    std::memcpy(vk + 448, ic.data(), 128);
-    checked = true;
-    ok = zkb_groth16_verify(vk, proof, witness.data() + 32) == ZKB_OK;
-  }
-  fprintf(stderr, "2^%u domain, %u variables: %.2f ms on the device; pairing check %s\n", zi.log_n, zi.n_vars, t.ms_total,
-          !checked ? "skipped (more than one public input)" : ok ? "passed" : "FAILED (witness does not satisfy the circuit?)");
+  uint8_t vk_fixed[448];
+  std::memcpy(vk_fixed, zd.alpha_g1, 64);
+  std::memcpy(vk_fixed + 64, zd.beta_g2, 128);
+  std::memcpy(vk_fixed + 192, zd.gamma_g2, 128);
+  std::memcpy(vk_fixed + 320, zd.delta_g2, 128);
+  const bool ok = zkb_groth16_verify_ex(vk_fixed, ic.data(), zi.n_public, proof, witness.data() + 32) == ZKB_OK;
+  fprintf(stderr, "2^%u domain, %u variables, %u public: %.2f ms on the device; pairing check %s\n", zi.log_n, zi.n_vars,
+          zi.n_public, t.ms_total, ok ? "passed" : "FAILED (witness does not satisfy the circuit?)");
   if (!ok) return 1;
   FILE* fp = fopen(argv[3], "w");
   FILE* fi = fopen(argv[4], "w");

@@ -292,6 +292,10 @@ int zkb_groth16_assemble_host(const uint8_t fixed[448], const uint8_t sums[ZKB_I
  * ZKB_EVERIFY = well-formed but invalid, ZKB_EINVAL = malformed (off-curve / non-canonical) */
 int zkb_groth16_verify(const uint8_t vk[ZKB_VK_BYTES], const uint8_t proof[ZKB_PROOF_BYTES],
                        const uint8_t public_input[32]);
+/* the same check for a key with any number of public inputs: vk_fixed = alpha_g1 64 | beta_g2 128 |
+ * gamma_g2 128 | delta_g2 128, ic = n_public + 1 G1 points, public_inputs = n_public canonical Fr */
+int zkb_groth16_verify_ex(const uint8_t vk_fixed[448], const uint8_t* ic, uint32_t n_public,
+                          const uint8_t proof[ZKB_PROOF_BYTES], const uint8_t* public_inputs);
 /* Strict well-formedness check of a proof / public input pair BEFORE it is handed to the settlement
  * layer (CPU, needs no key): the reference's parse_proof (src/settlement/ethereum/mod.rs:445-473)
  * accepts any U256, the contract then reverts (InvalidProof / NewStateRootNotInsidePrime,

@@ -158,6 +158,7 @@ extern "C" {
     pub fn zkb_groth16_prove_dist(ctx: *mut zkb_ctx, pk: *const zkb_pk, witness: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8, timings_opt: *mut zkb_prove_timings) -> c_int;
     pub fn zkb_groth16_assemble_host(fixed: *const u8, sums: *const u8, r: *const u8, s: *const u8, proof_out: *mut u8) -> c_int;
     pub fn zkb_groth16_verify(vk: *const u8, proof: *const u8, public_input: *const u8) -> c_int;
+    pub fn zkb_groth16_verify_ex(vk_fixed: *const u8, ic: *const u8, n_public: u32, proof: *const u8, public_inputs: *const u8) -> c_int;
     pub fn zkb_proof_check(proof: *const u8, public_input: *const u8, reasons_opt: *mut u32) -> c_int;
     pub fn zkb_selftest_final_exp(proof: *const u8) -> c_int;
     pub fn zkb_selftest_assemble_tables(fixed: *const u8, sums: *const u8, r: *const u8, s: *const u8) -> c_int;

@@ -402,3 +402,41 @@ def test_host_proof_assembly_matches_oracle(zkb):
     assert dt < 0.05
     with pytest.raises(zkb.ZkbError):
         zkb.lib.groth16_assemble_host(opk.fixed(), inter, fr_bytes([1]), int(o.R).to_bytes(32, "little"))
+
+
+def test_groth16_verify_ex_any_number_of_public_inputs(zkb):
+    """f2: the host verifier for keys with 0, 1 or several public inputs, against Oracle A proofs"""
+    import oracle_a as o
+    from helpers import small_circuit
+    g1s = lambda pts: b"".join(o.g1_to_bytes(P) for P in pts)
+    for n_pub in (0, 1, 3):
+        cs, z = small_circuit(5)
+        cs["n_pub"] = n_pub                        # wires 1..3 = out, x, y: any prefix can be public
+        rng = o.Xoshiro256ss(0xF2 + n_pub)
+        tau, alpha, beta, gamma, delta, r, s = [rng.fr() or 1 for _ in range(7)]
+        pk, vk = o.groth16_setup(cs, tau, alpha, beta, gamma, delta)
+        (A, B, C), _ = o.groth16_prove(pk, cs, z, r, s)
+        pub = z[1:1 + n_pub]
+        assert o.groth16_verify(vk, (A, B, C), pub)
+        fixed = o.g1_to_bytes(vk["alpha_g1"]) + o.g2_to_bytes(vk["beta_g2"]) + o.g2_to_bytes(vk["gamma_g2"]) + o.g2_to_bytes(vk["delta_g2"])
+        ic = g1s(vk["gamma_abc_g1"])
+        proof = o.g1_to_bytes(A) + o.g2_to_bytes(B) + o.g1_to_bytes(C)
+        inputs = b"".join(v.to_bytes(32, "little") for v in pub)
+        assert zkb.groth16_verify_ex(fixed, ic, proof, inputs)
+        if n_pub == 1:
+            assert zkb.groth16_verify(fixed + ic, proof, inputs)
+        for i in range(n_pub):                     # any single wrong input fails
+            bad = bytearray(inputs)
+            bad[32 * i] ^= 1
+            assert not zkb.groth16_verify_ex(fixed, ic, proof, bytes(bad))
+        other = o.g1_to_bytes(o.g1_add(A, o.G1_GEN)) + proof[64:]
+        assert not zkb.groth16_verify_ex(fixed, ic, other, inputs)
+        if n_pub:
+            with pytest.raises(zkb.ZkbError):      # an input >= r is malformed, not merely invalid
+                zkb.groth16_verify_ex(fixed, ic, proof, int(o.R).to_bytes(32, "little") + inputs[32:])
+            with pytest.raises(ValueError):
+                zkb.groth16_verify_ex(fixed, ic, proof, inputs[32:])
+        off = bytearray(ic)
+        off[0] ^= 1
+        with pytest.raises(zkb.ZkbError):          # ic0 off the curve
+            zkb.groth16_verify_ex(fixed, bytes(off), proof, inputs)

@@ -220,3 +220,23 @@ def test_zkey_entries_in_any_order_and_malformed_files(cio, zkb, zkey_case):
     bad(data[:s4 + 12] + struct.pack("<I", zk.n_vars) + data[s4 + 16:])
     bad(data[:s4 + 16] + o.R.to_bytes(32, "little") + data[s4 + 48:])
     bad(data[:s4] + struct.pack("<I", len(ref["coeffs"]) + 1) + data[s4 + 4:])   # count disagrees with the section size
+
+
+def test_zkey_with_three_public_inputs_through_reader_and_verify_ex(cio, zkb):
+    """the key-side bookkeeping for n_public != 1: four input rows in A, four IC points, a C section
+    without the instance variables; the oracle's snarkjs-style proof verifies through zkb_groth16_verify_ex"""
+    import oracle_zkey as zkm
+    cs, z = small_circuit(5)
+    cs["n_pub"] = 3
+    rng = o.Xoshiro256ss(77)
+    tau, alpha, beta, gamma, delta, r, s = [rng.fr() or 1 for _ in range(7)]
+    pk, vk = o.groth16_setup(cs, tau, alpha, beta, gamma, delta)
+    data = zkm.zkey_bytes(cs, pk, vk, zkm.h_points_snarkjs(tau, delta, pk["n"]))
+    zk, ref = cio.read_zkey(data), zkm.zkey_parse(data)
+    assert (zk.n_public, zk.n_rows, len(zk.ic), len(zk.queries["l_query"])) == (3, 5 + 4, 64 * 4, 64 * (cs["m"] - 4))
+    proof_pts, _ = zkm.groth16_prove_zkey(ref, z, r, s)
+    assert proof_pts == o.groth16_prove(pk, cs, z, r, s)[0]
+    proof = o.g1_to_bytes(proof_pts[0]) + o.g2_to_bytes(proof_pts[1]) + o.g1_to_bytes(proof_pts[2])
+    inputs = b"".join(v.to_bytes(32, "little") for v in z[1:4])
+    assert zkb.groth16_verify_ex(zk.vk_fixed(), zk.ic, proof, inputs)
+    assert not zkb.groth16_verify_ex(zk.vk_fixed(), zk.ic, proof, inputs[32:] + inputs[:32])
