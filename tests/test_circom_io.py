@@ -240,3 +240,36 @@ def test_zkey_with_three_public_inputs_through_reader_and_verify_ex(cio, zkb):
     inputs = b"".join(v.to_bytes(32, "little") for v in z[1:4])
     assert zkb.groth16_verify_ex(zk.vk_fixed(), zk.ic, proof, inputs)
     assert not zkb.groth16_verify_ex(zk.vk_fixed(), zk.ic, proof, inputs[32:] + inputs[:32])
+
+
+def test_zkey_parser_survives_mutated_files(cio, zkb, zkey_case):
+    """as for .r1cs / .wtns: truncations, byte flips, insertions, hostile lengths and counts end in an
+    accepted key or ZKB_EINVAL, never in a crash or an out-of-bounds write (read_zkey sizes every
+    buffer from zkb_zkey_inspect on the same bytes)"""
+    import random
+    data = zkey_case[6]
+    rng = random.Random(2)
+    rejected = accepted = 0
+    for it in range(3000):
+        b = bytearray(data)
+        kind = rng.randrange(5)
+        if kind == 0:
+            b = b[:rng.randrange(len(b) + 1)]
+        elif kind == 1:
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        elif kind == 2:
+            i = rng.randrange(len(b))
+            b[i:i] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 9)))
+        elif kind == 3:
+            i = rng.randrange(len(b) - 8)
+            b[i:i + 8] = rng.choice([0, 2**32 - 1, 2**64 - 1, 2**63, len(b), len(b) - i]).to_bytes(8, "little")
+        else:                                   # a 32-bit field (count, row, signal, n_vars, domain ...) goes wild
+            i = rng.randrange(len(b) - 4)
+            b[i:i + 4] = rng.choice([0, 1, 2**31, 2**32 - 1, 2**16]).to_bytes(4, "little")
+        try:
+            cio.read_zkey(bytes(b))
+            accepted += 1
+        except zkb.ZkbError:
+            rejected += 1
+    assert rejected > 1500 and accepted > 0
